@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Benchmark of the preprocessing / inversion hot path (BASELINE.json metric: audio-seconds per second).
+
+One "step" = one pass of the whole hot path over one batch of synthetic clips (config C4 of BASELINE.json:
+16384 clips x 4 s @ 22.05 kHz, n_fft 2048, hop 512, 128 mels), per GPU:
+
+    stage A  STFT + log-mel of every clip                         (P1 + P2)
+    stage B  MIDI notes -> 88-key onset piano roll @ 250 Hz -> audio-rate int8 planes (roll + onoff)   (P3)
+    stage C  32-iteration Griffin-Lim of every clip's magnitude spectrogram                             (P4)
+
+value = audio seconds in the batch / (time of A + B + C): the throughput of the full path; the per-stage figures and
+their rooflines are in "stages".  Inputs are resident in HBM for `value`; `e2e` repeats the step through the NumPy-facing
+public API with pinned HOST buffers (H2D of the audio / spectrograms / notes and D2H of every result inside the timed
+region).  N > 1: one process per GPU (torchrun), every rank runs its own shard of the same size (weak scaling), no
+data-path collective; time is the max over ranks.
+
+--impl reference times the CPU restatement of the reference's path (oracle/, NumPy float64 pocketfft -- librosa and
+pretty_midi are not installable in this image) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR, N_FFT, HOP, N_MELS, K = 22050, 2048, 512, 128, 1025
+CLIP_SECONDS = 4.0
+CLIP_LEN = int(SR * CLIP_SECONDS)          # 88200
+T_FRAMES = 1 + CLIP_LEN // HOP             # 173
+GL_ITERS = 32
+ROLL_FS, PITCH_LO, N_KEYS = 250, 21, 88
+METRIC = "audio-seconds/sec, STFT+log-mel + piano-roll + 32-iter Griffin-Lim (full hot path)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------------------------
+def make_notes(n_pieces, seed0):
+    """Host note arrays for n_pieces 4-second pieces (12 notes/s Poisson; SURVEY 8d C3 distribution)."""
+    from ml_music_style_transfer_b200 import synth
+    pool = [synth.midi_piece(seed0 + i, seconds=CLIP_SECONDS) for i in range(min(n_pieces, 256))]
+    pieces = [pool[i % len(pool)] for i in range(n_pieces)]
+    offs = np.zeros(n_pieces + 1, dtype=np.int64)
+    np.cumsum([len(p[0]) for p in pieces], out=offs[1:])
+    cat = lambda j, dt: np.concatenate([p[j] for p in pieces]).astype(dt)
+    return cat(0, np.int32), cat(1, np.int32), cat(2, np.float64), cat(3, np.float64), offs
+
+
+def make_audio_device(n_clips, device, seed0):
+    """Piano-like pool (host, seeded) tiled over the batch with per-clip gain + device noise floor."""
+    import torch
+    from ml_music_style_transfer_b200 import synth
+    pool = np.stack([synth.piano_clip(seed0 + i, CLIP_SECONDS, SR)[:CLIP_LEN] for i in range(64)])
+    pool_d = torch.from_numpy(pool).to(device)
+    g = torch.Generator(device=device).manual_seed(1234 + seed0)
+    audio = torch.empty(n_clips * CLIP_LEN, dtype=torch.float32, device=device)
+    view = audio.view(n_clips, CLIP_LEN)
+    for s in range(0, n_clips, 1024):
+        e = min(n_clips, s + 1024)
+        idx = torch.arange(s, e, device=device) % 64
+        gain = 0.5 + 0.5 * torch.rand(e - s, 1, generator=g, device=device)
+        view[s:e] = pool_d[idx] * gain + 1e-3 * torch.randn(e - s, CLIP_LEN, generator=g, device=device)
+    return audio
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ml_music_style_transfer_b200 as pkg
+    from ml_music_style_transfer_b200 import features as F, pianoroll as PR
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    pkg._lib.ops()
+    hbm_peak, peak_src = peaks()
+
+    n_clips = args.clips                      # per GPU (weak scaling)
+    audio_seconds = n_clips * CLIP_SECONDS
+    audio = make_audio_device(n_clips, device, seed0=1000 * rank)
+    batch = F.ClipBatch.uniform(n_clips, CLIP_LEN, HOP, device=device)
+    gl_batch = F.ClipBatch.from_frames([T_FRAMES] * n_clips, HOP, device=device)
+    plan = F.MelPlan.get(SR, N_FFT, N_MELS, device=device)
+    notes_h = make_notes(n_clips, seed0=99 + 1000 * rank)
+    roll_sub = min(n_clips, 1024)             # pieces per piano-roll launch (ring of output buffers)
+    notes = PR.NoteBatch(*notes_h, device=device)
+    # GL input: the magnitude spectrogram the model would emit (made once, untimed)
+    S = F.stft_batch(audio, batch, "magnitude", F.FRAME_MAJOR)
+    torch.cuda.synchronize()
+
+    def stage_a():
+        return F.melspectrogram_batch(audio, batch, plan, log1p=True, layout=F.BIN_MAJOR)
+
+    def stage_b():
+        roll, onoff, row_off, _ = PR.rasterize(notes, ROLL_FS)
+        outs = None
+        for s in range(0, n_clips, roll_sub):
+            e = min(n_clips, s + roll_sub)
+            ro = row_off[s:e + 1]
+            a, _ = PR.upsample(roll, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
+            b, _ = PR.upsample(onoff, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
+            outs = (a, b)
+        return outs
+
+    def stage_c(n_iter=GL_ITERS):
+        return F.griffinlim_batch(S, gl_batch, n_iter=n_iter, momentum=0.99, init_phase=None, init="random", seed=7,
+                                  layout=F.FRAME_MAJOR)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in evs:
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    # warm-up (W >= 3 steps)
+    for _ in range(max(3, args.warmup)):
+        stage_a(); stage_b(); stage_c()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = pkg._lib.launch_count()
+    ta, tb, tc = [], [], []
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        ta += timed(stage_a, 1); tb += timed(stage_b, 1); tc += timed(stage_c, 1)
+    ev1.record()
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    wall_s = time.perf_counter() - t_wall0
+    launches = pkg._lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # kernel-level roofline of the dominant kernel (Griffin-Lim iteration): (t[32 iters] - t[0 iters]) / 32
+    t0 = float(np.median(timed(lambda: stage_c(0), 3)))
+    t32 = float(np.median(tc))
+    iter_ms = (t32 - t0) / GL_ITERS
+    L = HOP * (T_FRAMES - 1)
+    gl_iter_bytes = n_clips * (36 * K * T_FRAMES + 8 * L)              # SURVEY 8d, per launch
+    gl_total_bytes = n_clips * (GL_ITERS * (36 * K * T_FRAMES + 8 * L) + 12 * K * T_FRAMES + 4 * L)
+    a_bytes = n_clips * (4 * CLIP_LEN + 4 * N_MELS * T_FRAMES)
+    b_bytes = n_clips * 2 * N_KEYS * CLIP_LEN
+    med = lambda x: float(np.median(x))
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, med(ta), med(tb), med(tc), iter_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, ma, mb, mc, iter_ms = [float(x) for x in t.tolist()]
+    else:
+        ma, mb, mc = med(ta), med(tb), med(tc)
+    ms_per_step = total_ms / args.steps
+    value = world * audio_seconds / (ms_per_step * 1e-3)
+
+    # ---- e2e: NumPy-facing API with pinned host buffers ------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, pkg, F, PR, device, audio, S, notes_h, plan, world, barrier)
+
+    if rank == 0:
+        stages = {
+            "stft_logmel": {"ms": ma, "audio_s_per_s": world * audio_seconds / (ma * 1e-3),
+                            "hbm_frac": a_bytes / (ma * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": a_bytes},
+            "pianoroll_upsample": {"ms": mb, "audio_s_per_s": world * audio_seconds / (mb * 1e-3),
+                                   "hbm_frac": b_bytes / (mb * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": b_bytes},
+            "griffinlim32": {"ms": mc, "audio_s_per_s": world * audio_seconds / (mc * 1e-3),
+                             "hbm_frac": gl_total_bytes / (mc * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": gl_total_bytes},
+        }
+        achieved = gl_iter_bytes / (iter_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C4: {n_clips} clips/GPU x 4 s @ 22.05 kHz, n_fft 2048, hop 512, 128 mels; "
+                                   f"88-key roll @ 250 Hz -> audio rate (int8, roll+onoff); Griffin-Lim {GL_ITERS} it",
+                       "clips_per_gpu": n_clips, "l2_policy": "inputs larger than L2 (5.8 GB audio, 11.6 GB spectrogram per GPU)",
+                       "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
+            "stages": stages,
+            "roofline": {"bound": "hbm", "kernel": "gl_kernel<false> (one Griffin-Lim iteration)", "achieved": achieved,
+                         "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "ms_per_launch": iter_ms, "algorithmic_bytes_per_launch": gl_iter_bytes, "traffic": args.traffic},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall_s,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cores=1, budget_s=args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrier):
+    """Same step through host buffers: pinned host -> device copies and device -> host reads are inside the timing."""
+    import torch
+    n = min(args.clips, args.e2e_clips)
+    h_audio = torch.empty(n * CLIP_LEN, dtype=torch.float32).pin_memory()
+    h_audio.copy_(audio_d[:n * CLIP_LEN])
+    h_S = torch.empty(n * T_FRAMES * K, dtype=torch.float32).pin_memory()
+    h_S.copy_(S_d[:n * T_FRAMES * K])
+    h_mel = torch.empty(n * N_MELS * T_FRAMES, dtype=torch.float32).pin_memory()
+    h_y = torch.empty(n * HOP * (T_FRAMES - 1), dtype=torch.float32).pin_memory()
+    sub = min(n, 256)
+    h_roll = torch.empty(2 * sub * N_KEYS * CLIP_LEN, dtype=torch.int8).pin_memory()
+    no = notes_h[4]
+    n_notes = int(no[n])
+    h_notes = [torch.from_numpy(np.ascontiguousarray(a[:n_notes])).pin_memory() for a in notes_h[:4]]
+    h_noff = torch.from_numpy(np.ascontiguousarray(no[:n + 1])).pin_memory()
+    batch = F.ClipBatch.uniform(n, CLIP_LEN, HOP, device=device)
+    gl_batch = F.ClipBatch.from_frames([T_FRAMES] * n, HOP, device=device)
+
+    def step():
+        a = h_audio.to(device, non_blocking=True)
+        mel = F.melspectrogram_batch(a, batch, plan, log1p=True, layout=F.BIN_MAJOR)
+        h_mel.copy_(mel, non_blocking=True)
+        nb = PR.NoteBatch.__new__(PR.NoteBatch)
+        nb.device = device
+        nb.pitch, nb.velocity, nb.start, nb.end = [t.to(device, non_blocking=True) for t in h_notes]
+        nb.note_offsets = h_noff.to(device, non_blocking=True)
+        nb.n_pieces = n
+        roll, onoff, row_off, _ = PR.rasterize(nb, ROLL_FS)
+        for s in range(0, n, sub):
+            e = min(n, s + sub)
+            ro = row_off[s:e + 1]
+            ua, _ = PR.upsample(roll, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
+            ub, _ = PR.upsample(onoff, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
+            m = (e - s) * N_KEYS * CLIP_LEN
+            h_roll[:m].copy_(ua, non_blocking=True)
+            h_roll[m:2 * m].copy_(ub, non_blocking=True)
+        Sd = h_S.to(device, non_blocking=True)
+        y = F.griffinlim_batch(Sd, gl_batch, n_iter=GL_ITERS, momentum=0.99, init="random", seed=7, layout=F.FRAME_MAJOR)
+        h_y.copy_(y, non_blocking=True)
+        torch.cuda.synchronize()
+
+    step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(1, min(args.steps, 3))
+    ev0.record()
+    for _ in range(reps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / reps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    h2d = h_audio.numel() * 4 + h_S.numel() * 4 + sum(t.numel() * t.element_size() for t in h_notes) + h_noff.numel() * 8
+    d2h = h_mel.numel() * 4 + h_y.numel() * 4 + 2 * n * N_KEYS * CLIP_LEN
+    return {"value": world * n * CLIP_SECONDS / (ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "clips_per_gpu": n, "ms_per_step": ms}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arms (oracle port of the reference's path)
+# ------------------------------------------------------------------------------------------------------------------
+def _cpu_clip_job(seed):
+    """Full hot path for ONE 4 s clip on one core; returns per-stage seconds."""
+    from ml_music_style_transfer_b200 import synth
+    from oracle import griffinlim as ogl, mel as omel, pianoroll as opr, stft as ostft
+    y = synth.piano_clip(seed, CLIP_SECONDS, SR)[:CLIP_LEN]
+    p, v, s, e = synth.midi_piece(seed, seconds=CLIP_SECONDS)
+    t0 = time.perf_counter()
+    omel.logmel(y, SR, N_FFT, HOP, N_MELS)
+    t1 = time.perf_counter()
+    roll, onoff = opr.binarize_and_onoff(opr.get_piano_roll(p, v, s, e, ROLL_FS))
+    opr.upsample_to_audio_rate(roll, ROLL_FS, SR, CLIP_LEN, PITCH_LO, N_KEYS)
+    opr.upsample_to_audio_rate(onoff, ROLL_FS, SR, CLIP_LEN, PITCH_LO, N_KEYS)
+    t2 = time.perf_counter()
+    S = np.abs(ostft.stft(y, N_FFT, HOP)).astype(np.float32)
+    t3 = time.perf_counter()
+    ogl.griffinlim(S, GL_ITERS, HOP, init_phase=ogl.random_phase(S.shape, seed))
+    t4 = time.perf_counter()
+    return t1 - t0, t2 - t1, t4 - t3
+
+
+def cpu_baseline(cores, budget_s):
+    """Oracle timed on a bounded sample of the same workload (whole 4 s clips through all three stages)."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    _cpu_clip_job(0)  # warm caches / imports
+    t0 = time.perf_counter()
+    n, acc = 0, np.zeros(3)
+    while time.perf_counter() - t0 < budget_s or n < 2:
+        acc += np.array(_cpu_clip_job(100 + n)); n += 1
+    wall = time.perf_counter() - t0
+    return {"value": n * CLIP_SECONDS / float(acc.sum()), "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "sample": f"{n} clips x 4 s (log-mel + piano-roll + GL-32 each), {wall:.1f} s of CPU work, single thread",
+            "stage_seconds_per_clip": {"stft_logmel": acc[0] / n, "pianoroll_upsample": acc[1] / n, "griffinlim32": acc[2] / n}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cores = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = "1"
+    per_step = max(cores, 8)  # clips per step: one per core
+    with mp.get_context("fork").Pool(cores) as pool:
+        for w in range(max(1, min(args.warmup, 1))):
+            pool.map(_cpu_clip_job, range(cores))
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            pool.map(_cpu_clip_job, range(1000 + k * per_step, 1000 + (k + 1) * per_step))
+        wall = time.perf_counter() - t0
+    value = args.steps * per_step * CLIP_SECONDS / wall
+    sample = f"{per_step} clips x 4 s per step (log-mel + piano-roll + GL-32 each), {cores} worker processes"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 clip shape: 4 s @ 22.05 kHz, n_fft 2048, hop 512, 128 mels; 88-key roll @ 250 Hz -> "
+                                   f"audio rate; Griffin-Lim {GL_ITERS} it (bounded sample)", "parallelism": f"{cores} host processes"},
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=16384, help="clips per GPU (C4: 16384)")
+    ap.add_argument("--e2e-clips", type=int, default=4096, help="clips per GPU for the host-buffer end-to-end pass")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per GL-iteration launch (from profiles/)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,381 @@
+// P4: Griffin-Lim phase reconstruction (librosa.griffinlim semantics; reference model/inference.py:105-110,
+// tests/test_griffinlim.py:23, classic loop at model/inference.py:131-154 == momentum 0).
+//
+// One kernel launch per iteration.  Launch j (j = 1..n_iter) does, per frame (one warp each):
+//   re-analysis   rebuilt_j = rfft(window * reflect_pad(y_{j-1})[t*hop : t*hop+2048])
+//   re-projection angles_j  = (rebuilt_j - a*rebuilt_{j-1}) / (|.| + 1e-16),  a = momentum / (1 + momentum)
+//   synthesis     y_j      += window * irfft(S * angles_j)            (overlap-add)
+// which is librosa's loop rotated by half an iteration: the launch before the first one synthesises y_0 from the
+// initial phase, and y_{n_iter} is librosa's final istft(S * angles).  State resident in HBM between launches:
+// the previous iterate rebuilt_{j-1} (complex64, read then overwritten in place by the same thread) and three
+// rotating overlap-add accumulators (read y_{j-1}, accumulate y_j, zero the one the next launch accumulates into).
+// The phase itself never touches HBM: it is recomputed from rebuilt_j and rebuilt_{j-1} in registers.
+//
+// Overlap-add: the 8 frames of a tile are summed in shared memory in frame order, the tile's span is then added to
+// the global accumulator with float atomics.  With hop >= 256 at most two tiles touch any sample and the buffer starts
+// at zero, so the result does not depend on the order the two adds land in (a + b == b + a): runs are reproducible.
+#include <algorithm>
+#include "fft_warp.cuh"
+#include "mst_common.cuh"
+
+namespace mst {
+
+struct GlParams {
+  const ClipDesc* clips;
+  const int32_t* tile_clip;
+  int total_tiles;
+  int hop;
+  int pad_mode;
+  Tables tabs;
+  const float* S;          // [total_frames][1025] magnitudes, frame-major
+  float2* tprev;           // [total_frames][1025] previous rebuilt spectrum
+  const float* inv_wss;    // 1 / window-sum-square envelopes
+  const int64_t* wss_off;  // per clip offset into inv_wss
+  const float* acc_in;     // y_{j-1} (un-normalised overlap-add sums)
+  float* acc_out;          // y_j accumulator (zero on entry)
+  float* acc_zero;         // accumulator of launch j+1: zeroed here
+  float alpha;             // momentum / (1 + momentum)
+  int first_iter;          // rebuilt_0 = 0: skip the tprev read
+  // init launch only
+  const float* init_phase; // uniform [0,1) field or NULL
+  int phase_layout;        // layout of init_phase
+  int init_mode;           // 0 random (device RNG when init_phase == NULL), 1 angles = 1
+  unsigned long long seed;
+};
+
+__device__ __forceinline__ float uniform_hash(unsigned long long seed, unsigned long long idx) {
+  // splitmix64 -> 24-bit mantissa uniform in [0,1)
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+// Inverse transform of one frame's spectrum, window, and park the 2048 samples in this warp's slot.
+__device__ __forceinline__ void synthesize_frame(float2 (&y)[32], float nyq, float2* scratch, const float2* s_tw1024,
+                                                 const float2* s_tw2048, const float* s_window, int lane) {
+  float2 v[32];
+  irfft2048_warp(y, nyq, v, scratch, s_tw1024, s_tw2048, lane);
+  __syncwarp();
+  const float2* w2 = reinterpret_cast<const float2*>(s_window);
+  const float scale = 1.0f / 1024.0f;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const float2 w = w2[lane + 32 * r];
+    const float2 z = v[br5(r)];
+    scratch[lane + 32 * r] = make_float2(z.x * scale * w.x, z.y * scale * w.y);  // samples 2m, 2m+1
+  }
+}
+
+// Sum the tile's frame slots in frame order and add the span to the global accumulator; zero the next accumulator.
+__device__ __forceinline__ void overlap_add_tile(const float* s_slots, const ClipDesc& cd, int t0, int hop,
+                                                 float* __restrict__ acc_out, float* __restrict__ acc_zero) {
+  const int nvalid = min(kWarpsPerCta, cd.frames - t0);
+  const int span = (nvalid - 1) * hop + kNfft;
+  float* dst = acc_out + cd.acc_offset + (int64_t)t0 * hop;
+  for (int p = threadIdx.x; p < span; p += blockDim.x) {
+    int f_lo = p - (kNfft - 1);
+    f_lo = f_lo > 0 ? (f_lo + hop - 1) / hop : 0;
+    const int f_hi = min(nvalid - 1, p / hop);
+    float sum = 0.0f;
+    for (int f = f_lo; f <= f_hi; ++f) sum += s_slots[f * (2 * kScratchPerWarp) + p - f * hop];
+    atomicAdd(dst + p, sum);
+  }
+  if (acc_zero) {
+    const int64_t acc_len = kNfft + (int64_t)hop * (cd.frames - 1);
+    const int64_t z0 = (int64_t)t0 * hop;
+    const bool last = t0 + kWarpsPerCta >= cd.frames;
+    const int64_t z1 = last ? acc_len : z0 + (int64_t)kWarpsPerCta * hop;
+    float* z = acc_zero + cd.acc_offset;
+    for (int64_t p = z0 + threadIdx.x; p < z1; p += blockDim.x) z[p] = 0.0f;
+  }
+}
+
+template <bool INIT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_tw1024 = reinterpret_cast<float2*>(smem_raw);
+  float2* s_tw2048 = s_tw1024 + 1024;
+  float* s_window = reinterpret_cast<float*>(s_tw2048 + 1024);
+  float2* s_scratch_all = reinterpret_cast<float2*>(s_window + kNfft);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* scratch = s_scratch_all + warp * kScratchPerWarp;
+
+  stage_tables(s_tw1024, s_tw2048, s_window, P.tabs.tw1024, P.tabs.tw2048, P.tabs.window);
+  __syncthreads();
+
+  for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    const int c = __ldg(P.tile_clip + tile);
+    const ClipDesc cd = P.clips[c];
+    const int t0 = (tile - cd.tile_offset) * kWarpsPerCta;
+    const int t = t0 + warp;
+    const bool active = t < cd.frames;
+    if (active) {
+      const int64_t row = (cd.frame_offset + t) * kBins;
+      float2 y[32];
+      float nyq;
+      if (INIT) {
+        // y_0 = istft(S * exp(2*pi*i*u))
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const int k = lane + 32 * r;
+          float sn = 0.0f, cs = 1.0f;
+          if (P.init_mode == 0) {
+            float u;
+            if (P.init_phase) {
+              const int64_t idx = P.phase_layout == MST_LAYOUT_FRAME_MAJOR
+                                      ? row + k
+                                      : cd.frame_offset * kBins + (int64_t)k * cd.frames + t;
+              u = __ldg(P.init_phase + idx);
+            } else {
+              u = uniform_hash(P.seed, (unsigned long long)(row + k));
+            }
+            sincospif(2.0f * u, &sn, &cs);
+          }
+          const float s = __ldg(P.S + row + k);
+          y[r] = make_float2(s * cs, s * sn);
+        }
+        {
+          float sn = 0.0f, cs = 1.0f;
+          if (P.init_mode == 0) {
+            float u;
+            if (P.init_phase) {
+              const int64_t idx = P.phase_layout == MST_LAYOUT_FRAME_MAJOR
+                                      ? row + 1024
+                                      : cd.frame_offset * kBins + (int64_t)1024 * cd.frames + t;
+              u = __ldg(P.init_phase + idx);
+            } else {
+              u = uniform_hash(P.seed, (unsigned long long)(row + 1024));
+            }
+            sincospif(2.0f * u, &sn, &cs);
+          }
+          nyq = __ldg(P.S + row + 1024) * cs;  // irfft ignores the imaginary part of the Nyquist bin
+        }
+      } else {
+        // ---- re-analysis of y_{j-1}: reflect-padded frame, normalised by the window-sum-square envelope ----
+        float2 v[32];
+        const int64_t L = cd.length;                         // hop * (T - 1)
+        const float* acc = P.acc_in + cd.acc_offset;         // acc[n + 1024] holds sample n before normalisation
+        const float* iw = P.inv_wss + __ldg(P.wss_off + c);
+        const int64_t base = (int64_t)t * P.hop - kHalf;  // first sample index of the frame (may be negative)
+        const bool interior = base >= 0 && base + kNfft <= L;
+        if (interior && ((base & 1) == 0)) {
+          const float2* a2 = reinterpret_cast<const float2*>(acc + base + kHalf);
+          const float2* w2 = reinterpret_cast<const float2*>(iw + base + kHalf);
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const float2 a = a2[32 * r + lane];
+            const float2 w = __ldg(w2 + 32 * r + lane);
+            v[r] = make_float2(a.x * w.x, a.y * w.y);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            float s[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              int64_t n = base + 2 * (32 * r + lane) + h;
+              bool ok = true;
+              if (n < 0) {
+                if (P.pad_mode == MST_PAD_REFLECT) n = -n; else ok = false;
+              } else if (n >= L) {
+                if (P.pad_mode == MST_PAD_REFLECT) n = 2 * (L - 1) - n; else ok = false;
+              }
+              s[h] = ok ? acc[n + kHalf] * __ldg(iw + n + kHalf) : 0.0f;
+            }
+            v[r] = make_float2(s[0], s[1]);
+          }
+        }
+        const float2* win2 = reinterpret_cast<const float2*>(s_window);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const float2 w = win2[32 * r + lane];
+          v[r].x *= w.x;
+          v[r].y *= w.y;
+        }
+        float xn;
+        rfft2048_warp(v, y, &xn, scratch, s_tw1024, s_tw2048, lane);
+        // ---- re-projection: momentum update, unit-modulus phase, target magnitude ----
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const int k = lane + 32 * r;
+          float2 tp = make_float2(0.0f, 0.0f);
+          if (!P.first_iter) tp = P.tprev[row + k];
+          P.tprev[row + k] = y[r];
+          const float ax = fmaf(-P.alpha, tp.x, y[r].x), ay = fmaf(-P.alpha, tp.y, y[r].y);
+          const float inv = 1.0f / (sqrtf(fmaf(ax, ax, ay * ay)) + 1e-16f);
+          const float s = __ldg(P.S + row + k);
+          y[r] = make_float2(s * ax * inv, s * ay * inv);
+        }
+        nyq = 0.0f;
+        if (lane == 0) {
+          float2 tp = make_float2(0.0f, 0.0f);
+          if (!P.first_iter) tp = P.tprev[row + 1024];
+          P.tprev[row + 1024] = make_float2(xn, 0.0f);
+          const float ax = fmaf(-P.alpha, tp.x, xn), ay = -P.alpha * tp.y;
+          const float inv = 1.0f / (sqrtf(fmaf(ax, ax, ay * ay)) + 1e-16f);
+          nyq = __ldg(P.S + row + 1024) * ax * inv;
+        }
+      }
+      synthesize_frame(y, nyq, scratch, s_tw1024, s_tw2048, s_window, lane);
+    }
+    __syncthreads();
+    overlap_add_tile(reinterpret_cast<const float*>(s_scratch_all), cd, t0, P.hop, P.acc_out, P.acc_zero);
+    __syncthreads();
+  }
+}
+
+// y[n] = acc[n + 1024] / wss[n + 1024]  (librosa.istft normalisation + centre trim)
+__global__ void gl_finalize_kernel(const ClipDesc* __restrict__ clips, int n_clips, const float* __restrict__ acc,
+                                   const float* __restrict__ inv_wss, const int64_t* __restrict__ wss_off,
+                                   float* __restrict__ y) {
+  const int c = blockIdx.y;
+  const ClipDesc cd = clips[c];
+  const float* a = acc + cd.acc_offset + kHalf;
+  const float* w = inv_wss + wss_off[c] + kHalf;
+  float* dst = y + cd.sample_offset;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < cd.length; n += (int64_t)gridDim.x * blockDim.x)
+    dst[n] = a[n] * __ldg(w + n);
+}
+
+// S ingest: any layout / log1p-power -> frame-major magnitudes.  One 32x32 tile per CTA (tiled transpose).
+__global__ void gl_ingest_kernel(const float* __restrict__ S_in, int layout, int is_log1p_power,
+                                 const ClipDesc* __restrict__ clips, float* __restrict__ S_out) {
+  __shared__ float tile[32][33];
+  const int c = blockIdx.z;
+  const ClipDesc cd = clips[c];
+  const int T = cd.frames;
+  const float* src = S_in + cd.frame_offset * kBins;
+  float* dst = S_out + cd.frame_offset * kBins;
+  for (int tb = blockIdx.x * 32; tb < T; tb += gridDim.x * 32) {
+    const int kb = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      float val = 0.0f;
+      if (layout == MST_LAYOUT_BIN_MAJOR) {
+        const int k = kb + i, t = tb + threadIdx.x;  // coalesced along t
+        if (k < kBins && t < T) val = src[(int64_t)k * T + t];
+      } else {
+        const int t = tb + i, k = kb + threadIdx.x;  // coalesced along k
+        if (k < kBins && t < T) val = src[(int64_t)t * kBins + k];
+      }
+      if (is_log1p_power) val = sqrtf(expm1f(fminf(fmaxf(val, 0.0f), 20.0f)));  // inference.py:109
+      tile[i][threadIdx.x] = val;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int t = tb + i, k = kb + threadIdx.x;
+      if (k < kBins && t < T) dst[(int64_t)t * kBins + k] = layout == MST_LAYOUT_BIN_MAJOR ? tile[threadIdx.x][i] : tile[i][threadIdx.x];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mst
+
+using namespace mst;
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" {
+
+size_t mst_griffinlim_workspace_bytes(const mst_batch_t* b) {
+  if (!b) return 0;
+  const size_t spec = (size_t)b->total_frames * kBins;
+  return align_up(spec * sizeof(float2), 256) + align_up(spec * sizeof(float), 256) +
+         3 * align_up((size_t)b->total_acc * sizeof(float), 256) + 256;
+}
+
+int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, const mst_batch_t* b, int n_iter,
+                       float momentum, const float* d_init_phase, int init_mode, uint64_t seed, float* d_y_out,
+                       void* d_workspace, size_t workspace_bytes, mst_stream_t stream) {
+  if (!d_S || !b || !d_y_out || !d_workspace) return fail(MST_ERR_INVALID, "mst_griffinlim_f32: null argument");
+  if (!b->from_frames || !b->d_inv_wss)
+    return fail(MST_ERR_INVALID, "mst_griffinlim_f32 needs a batch made by mst_batch_create_from_frames");
+  if (n_iter < 0) return fail(MST_ERR_INVALID, "n_iter must be >= 0");
+  if (s_layout != MST_LAYOUT_FRAME_MAJOR && s_layout != MST_LAYOUT_BIN_MAJOR) return fail(MST_ERR_INVALID, "bad layout");
+  if (init_mode != 0 && init_mode != 1) return fail(MST_ERR_INVALID, "bad init_mode");
+  if (workspace_bytes < mst_griffinlim_workspace_bytes(b))
+    return fail(MST_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, mst_griffinlim_workspace_bytes(b));
+  if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return fail(MST_ERR_INVALID, "workspace must be 256-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  Tables tabs;
+  int rc = get_tables(&tabs);
+  if (rc) return rc;
+
+  const size_t spec = (size_t)b->total_frames * kBins;
+  char* ws = reinterpret_cast<char*>(d_workspace);
+  float2* tprev = reinterpret_cast<float2*>(ws); ws += align_up(spec * sizeof(float2), 256);
+  float* S_t = reinterpret_cast<float*>(ws);     ws += align_up(spec * sizeof(float), 256);
+  const size_t acc_bytes = align_up((size_t)b->total_acc * sizeof(float), 256);
+  float* acc[3];
+  for (int i = 0; i < 3; ++i) { acc[i] = reinterpret_cast<float*>(ws); ws += acc_bytes; }
+
+  const float* S_use = d_S;
+  if (s_layout != MST_LAYOUT_FRAME_MAJOR || s_is_log1p_power) {
+    int max_T = 0;
+    for (int c = 0; c < b->n_clips; ++c) max_T = std::max(max_T, (int)b->h_clips[c].frames);
+    // gridDim.z is limited to 65535 clips per launch
+    for (int c0 = 0; c0 < b->n_clips; c0 += 65535) {
+      const int nc = std::min(65535, b->n_clips - c0);
+      dim3 grid((unsigned)std::min(64, (max_T + 31) / 32), (kBins + 31) / 32, (unsigned)nc);
+      gl_ingest_kernel<<<grid, dim3(32, 8), 0, s>>>(d_S, s_layout, s_is_log1p_power, b->d_clips + c0, S_t);
+      MST_CUDA_OK(cudaGetLastError());
+      count_launch();
+    }
+    S_use = S_t;
+  }
+
+  int dev = 0, sms = 0;
+  MST_CUDA_OK(cudaGetDevice(&dev));
+  MST_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = kTableBytes + sizeof(float2) * kScratchPerWarp * kWarpsPerCta;
+  static bool attr_set[64] = {false};
+  if (!attr_set[dev]) {
+    MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev] = true;
+  }
+  const int grid = std::min(b->total_tiles, 2 * sms);
+
+  MST_CUDA_OK(cudaMemsetAsync(acc[0], 0, acc_bytes, s));
+  MST_CUDA_OK(cudaMemsetAsync(acc[1], 0, acc_bytes, s));
+
+  GlParams P{};
+  P.clips = b->d_clips; P.tile_clip = b->d_tile_clip; P.total_tiles = b->total_tiles;
+  P.hop = b->hop; P.pad_mode = b->pad_mode; P.tabs = tabs;
+  P.S = S_use; P.tprev = tprev; P.inv_wss = b->d_inv_wss; P.wss_off = b->d_wss_offset;
+  P.alpha = momentum / (1.0f + momentum);
+  P.init_phase = d_init_phase; P.phase_layout = s_layout; P.init_mode = init_mode; P.seed = seed;
+
+  // launch 0: y_0 from the initial phase, accumulated into acc[0]
+  P.acc_in = nullptr; P.acc_out = acc[0]; P.acc_zero = nullptr; P.first_iter = 1;
+  gl_kernel<true><<<grid, kWarpsPerCta * 32, smem, s>>>(P);
+  MST_CUDA_OK(cudaGetLastError());
+  count_launch();
+  int cur = 0;
+  for (int j = 1; j <= n_iter; ++j) {
+    P.acc_in = acc[cur];
+    P.acc_out = acc[(cur + 1) % 3];
+    P.acc_zero = acc[(cur + 2) % 3];
+    P.first_iter = (j == 1);
+    gl_kernel<false><<<grid, kWarpsPerCta * 32, smem, s>>>(P);
+    MST_CUDA_OK(cudaGetLastError());
+    count_launch();
+    cur = (cur + 1) % 3;
+  }
+  {
+    int64_t max_len = 0;
+    for (int c = 0; c < b->n_clips; ++c) max_len = std::max(max_len, b->h_clips[c].length);
+    for (int c0 = 0; c0 < b->n_clips; c0 += 65535) {
+      const int nc = std::min(65535, b->n_clips - c0);
+      dim3 fgrid((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (max_len + 1023) / 1024)), (unsigned)nc);
+      gl_finalize_kernel<<<fgrid, 256, 0, s>>>(b->d_clips + c0, nc, acc[cur], b->d_inv_wss, b->d_wss_offset + c0, d_y_out);
+      MST_CUDA_OK(cudaGetLastError());
+      count_launch();
+    }
+  }
+  return MST_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// Shared host/device helpers for the mst_b200 kernels (error plumbing, device tables, batch layout).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/mst_b200.h"
+
+namespace mst {
+
+constexpr int kNfft = 2048;           // preprocess.py:25 / inference.py:105 -- the only n_fft the reference uses
+constexpr int kBins = kNfft / 2 + 1;  // 1025
+constexpr int kHalf = kNfft / 2;      // complex FFT length (even/odd packing) and centre padding
+constexpr int kWarpsPerCta = 8;
+constexpr int kScratchPerWarp = 32 * 33;  // float2 elements: padded 32x32 transpose tile == one 2048-sample frame slot
+
+// ---- error plumbing -----------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+#define MST_CUDA_OK(expr)                                                                     \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return ::mst::fail(MST_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                         __FILE__, __LINE__);                                                 \
+  } while (0)
+
+// ---- constant tables (per device, built once on the host in double precision) ----------------
+struct Tables {
+  const float2* tw1024;  // [32][32]: exp(-2*pi*i*k1*n2/1024)
+  const float2* tw2048;  // [1024]:   exp(-2*pi*i*k/2048)
+  const float* window;   // [2048]:   periodic Hann (scipy get_window('hann', 2048, fftbins=True))
+};
+int get_tables(Tables* out);  // for the current device
+constexpr int kTableBytes = 1024 * 8 + 1024 * 8 + 2048 * 4;  // 24 KB staged in shared memory
+
+// ---- batch descriptor -------------------------------------------------------------------------
+struct ClipDesc {        // one per clip, device resident
+  int64_t sample_offset; // first sample of the clip in the audio buffer
+  int64_t length;        // samples
+  int64_t frame_offset;  // prefix sum of frames
+  int64_t acc_offset;    // Griffin-Lim overlap-add accumulator offset (floats)
+  int32_t frames;        // T = 1 + length / hop
+  int32_t tile_offset;   // prefix sum of ceil(T / kWarpsPerCta)
+};
+
+}  // namespace mst
+
+struct mst_batch {
+  int n_clips = 0;
+  int n_fft = 0, hop = 0, pad_mode = 0;
+  int64_t total_frames = 0, total_samples = 0, total_acc = 0;
+  int total_tiles = 0;
+  int device = 0;
+  bool from_frames = false;
+  mst::ClipDesc* h_clips = nullptr;  // host copy
+  mst::ClipDesc* d_clips = nullptr;  // device copy
+  int32_t* d_tile_clip = nullptr;    // [total_tiles] clip id of each frame tile
+  float* d_inv_wss = nullptr;        // Griffin-Lim: 1 / window-sum-square per accumulator position (shared by equal-T clips)
+  int64_t* d_wss_offset = nullptr;   // [n_clips] offset of the clip's envelope inside d_inv_wss
+};

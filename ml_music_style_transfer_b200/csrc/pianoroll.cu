@@ -1,0 +1,236 @@
+// P3: MIDI notes -> 128-pitch piano roll -> binarise -> on/off -> chunks / audio-rate planes.
+// Integer / byte work, bit-exact against pretty_midi's get_piano_roll (notes only) followed by the
+// NumPy lines of reference preprocessing/preprocess.py:146-155 and :80-96; the audio-rate
+// hold-replication is the README-only step (README.md:19-20) as defined in SURVEY section 8a P3d.
+// All of it is HBM-bound: the frame-rate roll is tiny, the audio-rate planes are a pure write stream
+// (128-bit coalesced stores).
+#include <algorithm>
+#include "mst_common.cuh"
+
+namespace mst {
+
+// int(t * fs) as Python evaluates it: IEEE double product (no FMA contraction), truncation toward zero.
+__device__ __forceinline__ int64_t col_of(double t, int fs) { return (int64_t)__dmul_rn(t, (double)fs); }
+
+__global__ void count_rows_kernel(const double* __restrict__ end, const int64_t* __restrict__ note_off, int n_pieces,
+                                  int fs, int64_t* __restrict__ rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_pieces) return;
+  const int64_t a = note_off[warp], b = note_off[warp + 1];
+  double m = 0.0;
+  bool any = false;
+  for (int64_t i = a + lane; i < b; i += 32) {
+    const double e = end[i];
+    m = any ? fmax(m, e) : e;
+    any = true;
+  }
+  for (int o = 16; o; o >>= 1) {
+    const double mo = __shfl_xor_sync(0xffffffffu, m, o);
+    const bool ao = __shfl_xor_sync(0xffffffffu, (int)any, o);
+    if (ao) { m = any ? fmax(m, mo) : mo; any = true; }
+  }
+  if (lane == 0) {
+    int64_t T = any ? col_of(m, fs) : 0;  // int(fs * end_time)
+    rows[warp] = T < 0 ? 0 : T;
+  }
+}
+
+// One warp per note: mark [int(start*fs), int(end*fs)) in the time-major roll of its piece.
+__global__ void rasterize_kernel(const int32_t* __restrict__ pitch, const int32_t* __restrict__ vel,
+                                 const double* __restrict__ start, const double* __restrict__ end,
+                                 const int64_t* __restrict__ note_off, int n_pieces,
+                                 const int64_t* __restrict__ row_off, int64_t total_notes, int fs,
+                                 uint8_t* __restrict__ roll, int32_t* __restrict__ velsum) {
+  const int64_t note = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (note >= total_notes) return;
+  // piece = last p with note_off[p] <= note
+  int lo = 0, hi = n_pieces;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (note_off[mid] <= note) lo = mid; else hi = mid;
+  }
+  const int64_t r0 = row_off[lo], T = row_off[lo + 1] - r0;
+  const int p = pitch[note], v = vel[note];
+  if (p < 0 || p > 127 || v == 0) return;
+  int64_t s = col_of(start[note], fs), e = col_of(end[note], fs);
+  if (s < 0) s = 0;  // pretty_midi never produces negative note times
+  if (e > T) e = T;  // NumPy slice clipping
+  for (int64_t c = s + lane; c < e; c += 32) {
+    const int64_t idx = (r0 + c) * 128 + p;
+    roll[idx] = 1;
+    if (velsum) atomicAdd(velsum + idx, v);
+  }
+}
+
+// onoff[i] = roll[i] - roll[i-1] with a zero row before the first row of each piece (preprocess.py:149-155).
+__global__ void onoff_kernel(const uint8_t* __restrict__ roll, const int64_t* __restrict__ row_off, int n_pieces,
+                             int8_t* __restrict__ onoff) {
+  for (int p = blockIdx.y; p < n_pieces; p += gridDim.y) {
+    const int64_t r0 = row_off[p], T = row_off[p + 1] - r0;
+    const uint4* src = reinterpret_cast<const uint4*>(roll + r0 * 128);
+    uint4* dst = reinterpret_cast<uint4*>(onoff + r0 * 128);
+    const int64_t nvec = T * 8;  // 128 bytes per row = 8 x 16 B
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+      const uint4 cur = src[i];
+      uint4 prev = make_uint4(0, 0, 0, 0);
+      if (i >= 8) prev = src[i - 8];
+      uint4 o;
+      // bytes are 0/1: per-byte subtraction without borrow across lanes -> __vsub4
+      o.x = __vsub4(cur.x, prev.x); o.y = __vsub4(cur.y, prev.y);
+      o.z = __vsub4(cur.z, prev.z); o.w = __vsub4(cur.w, prev.w);
+      dst[i] = o;
+    }
+  }
+}
+
+template <typename OUT>
+__global__ void chunks_kernel(const int8_t* __restrict__ plane, int64_t n_rows, int num_chunks, int chunk_rows,
+                              int stride_rows, OUT* __restrict__ out) {
+  const int64_t total = (int64_t)num_chunks * chunk_rows * 128;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i & 127);
+    const int64_t rj = i >> 7;
+    const int64_t c = rj / chunk_rows, j = rj - c * chunk_rows;
+    const int64_t row = c * stride_rows + j;
+    out[i] = row < n_rows ? (OUT)plane[row * 128 + p] : (OUT)0;
+  }
+}
+
+// Audio-rate hold-replication.  Each thread produces one 16-byte vector of one key row; rows are written with
+// aligned 128-bit stores (scalar head / tail where a row does not start on a 16-byte boundary).
+template <typename OUT>
+__global__ void upsample_kernel(const int8_t* __restrict__ plane, const int64_t* __restrict__ row_off,
+                                const int64_t* __restrict__ samp_off, int n_pieces, int fs, int sr, int pitch_lo,
+                                int n_keys, OUT* __restrict__ out) {
+  constexpr int EPV = 16 / sizeof(OUT);
+  for (int piece = blockIdx.z; piece < n_pieces; piece += gridDim.z) {
+    const int64_t r0 = row_off[piece], T = row_off[piece + 1] - r0;
+    const int64_t N = samp_off[piece + 1] - samp_off[piece];
+    const int8_t* src = plane + r0 * 128 + pitch_lo;
+    for (int k = blockIdx.y; k < n_keys; k += gridDim.y) {
+      OUT* row = out + samp_off[piece] * n_keys + (int64_t)k * N;
+      const int64_t mis = (int64_t)(((16 - (reinterpret_cast<uintptr_t>(row) & 15)) & 15) / sizeof(OUT));
+      const int64_t head = mis < N ? mis : N;
+      const int64_t nvec = (N - head) / EPV;
+      const int64_t tail0 = head + nvec * EPV;
+      // vector v covers samples [head + v*EPV, +EPV); pseudo-vectors nvec (head) and nvec+1 (tail) are scalar
+      for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec + 2; v += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n0, cnt;
+        if (v < nvec) { n0 = head + v * EPV; cnt = EPV; }
+        else if (v == nvec) { n0 = 0; cnt = head; }
+        else { n0 = tail0; cnt = N - tail0; }
+        if (cnt <= 0) continue;
+        int64_t col = (n0 * fs) / sr;
+        int64_t rem = n0 * fs - col * sr;
+        OUT vals[EPV];
+        int8_t cur = col < T ? src[col * 128 + k] : (int8_t)0;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          vals[e] = (OUT)cur;
+          rem += fs;
+          if (rem >= sr) {
+            do { rem -= sr; ++col; } while (rem >= sr);
+            cur = col < T ? src[col * 128 + k] : (int8_t)0;
+          }
+        }
+        if (cnt == EPV && v < nvec) {
+          *reinterpret_cast<uint4*>(row + n0) = *reinterpret_cast<const uint4*>(vals);
+        } else {
+          for (int e = 0; e < cnt; ++e) row[n0 + e] = vals[e];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace mst
+
+using namespace mst;
+
+extern "C" {
+
+int mst_pianoroll_count_rows(const double* d_end, const int64_t* d_note_offsets, int n_pieces, int fs,
+                             int64_t* d_rows_out, mst_stream_t stream) {
+  if (!d_end || !d_note_offsets || !d_rows_out) return fail(MST_ERR_INVALID, "null argument");
+  if (n_pieces <= 0 || fs <= 0) return fail(MST_ERR_INVALID, "n_pieces and fs must be positive");
+  const int threads = 256, warps_per_block = threads / 32;
+  count_rows_kernel<<<(n_pieces + warps_per_block - 1) / warps_per_block, threads, 0,
+                      reinterpret_cast<cudaStream_t>(stream)>>>(d_end, d_note_offsets, n_pieces, fs, d_rows_out);
+  MST_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return MST_OK;
+}
+
+int mst_pianoroll_rasterize(const int32_t* d_pitch, const int32_t* d_velocity, const double* d_start,
+                            const double* d_end, const int64_t* d_note_offsets, int n_pieces,
+                            const int64_t* d_row_offsets, int64_t total_rows, int64_t total_notes, int fs,
+                            uint8_t* d_roll, int8_t* d_onoff, int32_t* d_velsum, mst_stream_t stream) {
+  if (!d_pitch || !d_velocity || !d_start || !d_end || !d_note_offsets || !d_row_offsets || !d_roll || !d_onoff)
+    return fail(MST_ERR_INVALID, "null argument");
+  if (n_pieces <= 0 || fs <= 0 || total_rows < 0 || total_notes < 0) return fail(MST_ERR_INVALID, "bad sizes");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (total_rows == 0) return MST_OK;
+  if (reinterpret_cast<uintptr_t>(d_roll) & 15 || reinterpret_cast<uintptr_t>(d_onoff) & 15)
+    return fail(MST_ERR_INVALID, "roll / onoff must be 16-byte aligned");
+  MST_CUDA_OK(cudaMemsetAsync(d_roll, 0, (size_t)total_rows * 128, s));
+  if (d_velsum) MST_CUDA_OK(cudaMemsetAsync(d_velsum, 0, (size_t)total_rows * 128 * sizeof(int32_t), s));
+  if (total_notes > 0) {
+    const int threads = 256;
+    const int64_t blocks = (total_notes * 32 + threads - 1) / threads;
+    rasterize_kernel<<<(unsigned)blocks, threads, 0, s>>>(d_pitch, d_velocity, d_start, d_end, d_note_offsets, n_pieces,
+                                                           d_row_offsets, total_notes, fs, d_roll, d_velsum);
+    MST_CUDA_OK(cudaGetLastError());
+    count_launch();
+  }
+  dim3 grid(64, (unsigned)std::min(n_pieces, 65535));
+  onoff_kernel<<<grid, 256, 0, s>>>(d_roll, d_row_offsets, n_pieces, d_onoff);
+  MST_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return MST_OK;
+}
+
+int mst_pianoroll_chunks(const void* d_plane, int64_t n_rows, int num_chunks, int chunk_rows, int stride_rows,
+                         int out_dtype, void* d_out, mst_stream_t stream) {
+  if (!d_plane || !d_out) return fail(MST_ERR_INVALID, "null argument");
+  if (num_chunks < 0 || chunk_rows <= 0 || stride_rows <= 0 || n_rows < 0) return fail(MST_ERR_INVALID, "bad sizes");
+  if (num_chunks == 0) return MST_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)num_chunks * chunk_rows * 128;
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  const int8_t* src = reinterpret_cast<const int8_t*>(d_plane);
+  switch (out_dtype) {
+    case MST_DTYPE_I8: chunks_kernel<int8_t><<<blocks, 256, 0, s>>>(src, n_rows, num_chunks, chunk_rows, stride_rows, (int8_t*)d_out); break;
+    case MST_DTYPE_F32: chunks_kernel<float><<<blocks, 256, 0, s>>>(src, n_rows, num_chunks, chunk_rows, stride_rows, (float*)d_out); break;
+    case MST_DTYPE_F64: chunks_kernel<double><<<blocks, 256, 0, s>>>(src, n_rows, num_chunks, chunk_rows, stride_rows, (double*)d_out); break;
+    default: return fail(MST_ERR_INVALID, "bad out_dtype %d", out_dtype);
+  }
+  MST_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return MST_OK;
+}
+
+int mst_pianoroll_upsample(const void* d_plane, const int64_t* d_row_offsets, const int64_t* d_sample_offsets,
+                           int n_pieces, int64_t total_samples, int fs, int sr, int pitch_lo, int n_keys, int out_dtype,
+                           void* d_out, mst_stream_t stream) {
+  if (!d_plane || !d_row_offsets || !d_sample_offsets || !d_out) return fail(MST_ERR_INVALID, "null argument");
+  if (n_pieces <= 0 || fs <= 0 || sr <= 0 || pitch_lo < 0 || n_keys <= 0 || pitch_lo + n_keys > 128)
+    return fail(MST_ERR_INVALID, "bad upsample geometry");
+  if (total_samples <= 0) return MST_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t avg = total_samples / n_pieces + 1;
+  const int epv = out_dtype == MST_DTYPE_I8 ? 16 : 4;
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (avg / epv + 255) / 256));
+  dim3 grid(gx, (unsigned)n_keys, (unsigned)std::min(n_pieces, 65535));
+  const int8_t* src = reinterpret_cast<const int8_t*>(d_plane);
+  switch (out_dtype) {
+    case MST_DTYPE_I8: upsample_kernel<int8_t><<<grid, 256, 0, s>>>(src, d_row_offsets, d_sample_offsets, n_pieces, fs, sr, pitch_lo, n_keys, (int8_t*)d_out); break;
+    case MST_DTYPE_F32: upsample_kernel<float><<<grid, 256, 0, s>>>(src, d_row_offsets, d_sample_offsets, n_pieces, fs, sr, pitch_lo, n_keys, (float*)d_out); break;
+    default: return fail(MST_ERR_UNSUPPORTED, "upsample out_dtype must be int8 or float32");
+  }
+  MST_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return MST_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+"""Host-side operators of the hot path: thin Python over ``torch.ops.mst_b200`` (which wraps the C ABI).
+
+Names and defaults follow the third-party entry points the reference calls
+(``librosa.stft`` preprocess.py:48, ``librosa.feature.melspectrogram`` tests/plot_spec.py:20,
+``librosa.filters.mel``, ``librosa.griffinlim`` model/inference.py:110) so that the drop-in
+modules ``preprocess`` / ``inference`` read like the reference.  NumPy in -> NumPy out (host<->device
+copies included, as the reference's users expect); CUDA tensor in -> CUDA tensor out, no host round trip.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+N_FFT = 2048
+N_BINS = N_FFT // 2 + 1
+
+OUT_COMPLEX, OUT_MAGNITUDE, OUT_POWER, OUT_LOG1P_POWER = 0, 1, 2, 3
+FRAME_MAJOR, BIN_MAJOR = 0, 1
+PAD_MODES = {"reflect": 0, "constant": 1}
+DTYPE_CODES = {torch.int8: 0, torch.float32: 1, torch.float64: 2}
+
+
+def _pad_code(pad_mode):
+    try:
+        return PAD_MODES[pad_mode]
+    except KeyError:
+        raise ValueError(f"pad_mode={pad_mode!r} unsupported (reflect | constant)") from None
+
+
+def _check_window(window, win_length, n_fft):
+    if window != "hann":
+        raise NotImplementedError("only window='hann' is implemented (the reference uses no other)")
+    if n_fft != N_FFT:
+        raise NotImplementedError("n_fft=2048 is the only size the reference uses and the only one built")
+    if win_length not in (None, n_fft):
+        raise NotImplementedError("win_length must equal n_fft")
+
+
+class ClipBatch:
+    """Ragged set of clips inside one audio buffer (``mst_batch_t``).  Chunks may overlap."""
+
+    def __init__(self, handle, n_clips, hop, device):
+        self.handle, self.n_clips, self.hop, self.device = handle, n_clips, hop, device
+        o = _lib.ops()
+        self.total_frames = int(o.batch_total_frames(handle))
+        self.total_samples = int(o.batch_total_samples(handle))
+
+    @classmethod
+    def from_clips(cls, offsets, lengths, hop, pad_mode="reflect", device=None, n_fft=N_FFT):
+        device = _lib.require_cuda(device)
+        offsets = torch.as_tensor(np.asarray(offsets, dtype=np.int64))
+        lengths = torch.as_tensor(np.asarray(lengths, dtype=np.int64))
+        h = _lib.ops().batch_create(offsets, lengths, n_fft, int(hop), _pad_code(pad_mode), device.index)
+        return cls(h, int(offsets.numel()), int(hop), device)
+
+    @classmethod
+    def uniform(cls, n_clips, clip_length, hop, clip_stride=None, pad_mode="reflect", device=None):
+        stride = clip_length if clip_stride is None else clip_stride
+        offsets = np.arange(n_clips, dtype=np.int64) * stride
+        return cls.from_clips(offsets, np.full(n_clips, clip_length, dtype=np.int64), hop, pad_mode, device)
+
+    @classmethod
+    def from_frames(cls, frames_per_clip, hop, pad_mode="reflect", device=None, n_fft=N_FFT):
+        device = _lib.require_cuda(device)
+        frames = torch.as_tensor(np.asarray(frames_per_clip, dtype=np.int64))
+        h = _lib.ops().batch_create_from_frames(frames, n_fft, int(hop), _pad_code(pad_mode), device.index)
+        return cls(h, int(frames.numel()), int(hop), device)
+
+    def clip_frames(self, c):
+        return int(_lib.ops().batch_clip_frames(self.handle, c))
+
+    def close(self):
+        if getattr(self, "handle", 0):
+            _lib.ops().batch_destroy(self.handle)
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MelPlan:
+    """Device-resident filterbank (``mst_mel_plan_t``) built from librosa.filters.mel semantics."""
+
+    _cache = {}
+
+    def __init__(self, weights, device):
+        self.weights = weights  # CPU float32 (n_mels, 1025)
+        self.n_mels = int(weights.shape[0])
+        self.device = device
+        self.handle = _lib.ops().mel_plan_create(weights.contiguous(), device.index)
+
+    @classmethod
+    def get(cls, sr, n_fft=N_FFT, n_mels=128, fmin=0.0, fmax=None, device=None):
+        device = _lib.require_cuda(device)
+        key = (int(sr), int(n_fft), int(n_mels), float(fmin), None if fmax is None else float(fmax), device.index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(mel_filterbank(sr, n_fft, n_mels, fmin, fmax), device)
+        return cls._cache[key]
+
+
+def mel_filterbank(sr, n_fft=N_FFT, n_mels=128, fmin=0.0, fmax=None):
+    """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False, norm='slaney') -> CPU float32 (n_mels, 1+n_fft/2)."""
+    return _lib.ops().mel_filterbank(int(sr), int(n_fft), int(n_mels), float(fmin), 0.0 if fmax is None else float(fmax))
+
+
+def _to_device_audio(y, device=None):
+    """Returns (float32 CUDA 1-D tensor, was_numpy)."""
+    if isinstance(y, torch.Tensor):
+        if not y.is_cuda:
+            raise TypeError("torch inputs must be CUDA tensors (there is no CPU path); pass NumPy for host data")
+        return y.to(torch.float32).contiguous().view(-1), False
+    device = _lib.require_cuda(device)
+    a = np.ascontiguousarray(y, dtype=np.float32).reshape(-1)
+    return torch.from_numpy(a).to(device, non_blocking=False), True
+
+
+def stft_batch(audio, batch, out="log1p_power", layout=FRAME_MAJOR):
+    """Raw batched op.  ``audio``: CUDA float32 buffer; returns the flat output tensor of mst_stft_f32."""
+    mode = {"complex": OUT_COMPLEX, "magnitude": OUT_MAGNITUDE, "power": OUT_POWER, "log1p_power": OUT_LOG1P_POWER}[out]
+    return _lib.ops().stft(audio, batch.handle, mode, layout)
+
+
+def melspectrogram_batch(audio, batch, plan, log1p=False, layout=FRAME_MAJOR):
+    return _lib.ops().stft_mel(audio, batch.handle, plan.handle, plan.n_mels, bool(log1p), layout)
+
+
+def stft(y, n_fft=N_FFT, hop_length=None, win_length=None, window="hann", center=True, pad_mode="reflect"):
+    """librosa.stft drop-in for one clip: complex64 (1025, T), Fortran-ordered like librosa's result."""
+    _check_window(window, win_length, n_fft)
+    if not center:
+        raise NotImplementedError("center=False is not used by the reference")
+    hop = n_fft // 4 if hop_length is None else int(hop_length)
+    a, was_np = _to_device_audio(y)
+    b = ClipBatch.uniform(1, a.numel(), hop, pad_mode=pad_mode, device=a.device)
+    out = stft_batch(a, b, "complex").t()  # (1025, T) view over [T][1025] memory == Fortran order
+    b.close()
+    return out.cpu().numpy() if was_np else out
+
+
+def spectrogram(y, hop_length, out="log1p_power", pad_mode="reflect"):
+    """(1025, T) float32 epilogue of the STFT for one clip (Fortran-ordered view)."""
+    a, was_np = _to_device_audio(y)
+    b = ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device)
+    o = stft_batch(a, b, out).view(b.total_frames, N_BINS).t()
+    b.close()
+    return o.cpu().numpy() if was_np else o
+
+
+def melspectrogram(y=None, sr=22050, n_fft=N_FFT, hop_length=512, n_mels=128, fmin=0.0, fmax=None, pad_mode="reflect",
+                   log1p=False):
+    """librosa.feature.melspectrogram(y=, sr=, n_fft=, hop_length=) drop-in: float32 (n_mels, T)."""
+    _check_window("hann", None, n_fft)
+    a, was_np = _to_device_audio(y)
+    plan = MelPlan.get(sr, n_fft, n_mels, fmin, fmax, a.device)
+    b = ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device)
+    o = melspectrogram_batch(a, b, plan, log1p=log1p, layout=BIN_MAJOR).view(n_mels, b.total_frames)
+    b.close()
+    return o.cpu().numpy() if was_np else o
+
+
+def logmel(y, sr=22050, n_fft=N_FFT, hop_length=512, n_mels=128, **kw):
+    """log1p(mel_basis @ |stft|^2): the reference's log1p convention (preprocess.py:49) on the mel projection."""
+    return melspectrogram(y=y, sr=sr, n_fft=n_fft, hop_length=hop_length, n_mels=n_mels, log1p=True, **kw)
+
+
+def griffinlim_batch(S, batch, n_iter=32, momentum=0.99, init_phase=None, init="random", seed=0, layout=BIN_MAJOR,
+                     is_log1p_power=False):
+    """Raw batched op: S is a flat / shaped CUDA float32 tensor holding every clip's (1025 x T_c) block in `layout`."""
+    init_mode = {"random": 0, None: 1}[init]
+    return _lib.ops().griffinlim(S.contiguous().view(-1), layout, bool(is_log1p_power), batch.handle, int(n_iter),
+                                 float(momentum), None if init_phase is None else init_phase.contiguous().view(-1),
+                                 init_mode, int(seed))
+
+
+def griffinlim(S, n_iter=32, hop_length=None, win_length=None, window="hann", momentum=0.99, init="random",
+               random_state=None, init_phase=None, pad_mode="reflect"):
+    """librosa.griffinlim drop-in for one (1025, T) magnitude spectrogram -> float32 waveform of hop*(T-1) samples.
+
+    ``random_state=int`` reproduces librosa's ``RandomState(seed).rand(*S.shape)`` initial phase exactly (drawn on the
+    host); ``init_phase`` supplies the uniform [0,1) field directly; otherwise the phase comes from the device RNG.
+    """
+    was_np = not isinstance(S, torch.Tensor)
+    device = _lib.require_cuda(None if was_np else S.device)
+    if was_np:
+        S = torch.from_numpy(np.ascontiguousarray(S, dtype=np.float32)).to(device)
+    if S.dim() != 2 or S.shape[0] != N_BINS:
+        raise ValueError(f"S must be (1025, T); got {tuple(S.shape)}")
+    n_fft = 2 * (S.shape[0] - 1)
+    _check_window(window, win_length, n_fft)
+    hop = n_fft // 4 if hop_length is None else int(hop_length)
+    T = int(S.shape[1])
+    if init_phase is None and init == "random" and isinstance(random_state, (int, np.integer)):
+        init_phase = np.random.RandomState(int(random_state)).rand(N_BINS, T)
+    if init_phase is not None and not isinstance(init_phase, torch.Tensor):
+        init_phase = torch.from_numpy(np.ascontiguousarray(init_phase, dtype=np.float32)).to(device)
+    # a (1025,T) tensor whose memory is [T][1025] (librosa's Fortran order) is consumed without a transpose
+    if S.stride() == (1, N_BINS) and (init_phase is None or init_phase.stride() == (1, N_BINS)):
+        layout, S_flat = FRAME_MAJOR, S.t()
+        ph = None if init_phase is None else init_phase.t()
+    else:
+        layout, S_flat = BIN_MAJOR, S.contiguous()
+        ph = None if init_phase is None else init_phase.to(torch.float32).contiguous()
+    b = ClipBatch.from_frames([T], hop, pad_mode=pad_mode, device=device)
+    y = griffinlim_batch(S_flat.to(torch.float32), b, n_iter, momentum, ph, init, 0 if random_state is None else 0,
+                         layout)
+    b.close()
+    return y.cpu().numpy() if was_np else y
+
+
+def spectral_convergence(S, y, hop_length, pad_mode="reflect"):
+    """|| |STFT(y)| - S ||_F / ||S||_F on the device (normalised form of model/inference.py:149-150)."""
+    a, _ = _to_device_audio(y)
+    if not isinstance(S, torch.Tensor):
+        S = torch.from_numpy(np.ascontiguousarray(S, dtype=np.float32)).to(a.device)
+    R = spectrogram(a, hop_length, out="magnitude", pad_mode=pad_mode)
+    return float(torch.linalg.norm(R.double() - S.double()) / torch.linalg.norm(S.double()))

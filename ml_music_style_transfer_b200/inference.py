@@ -1,0 +1,69 @@
+"""Drop-in for the hot-path methods of the reference's ``model/inference.py::AudioSynthesizer``.
+
+Only the path members are reproduced: the Griffin-Lim inversion (inference.py:105-110) and the MIDI / audio
+conditioning inputs (inference.py:37-57).  The PerformanceNet forward pass stays stock PyTorch and is out of scope.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, features
+from .preprocess import hyperparams, notes_to_pianoroll, process_spectrum_from_chunk
+from .midi import read_midi_notes
+
+pp_hp = hyperparams()
+
+
+class AudioSynthesizer():
+    def __init__(self, checkpoint=None, exp_dir=None, midi_source=None, audio_source=None):
+        # inference.py:23-29; the checkpoint is only read when somebody asks for it (model is out of scope)
+        self.exp_dir = exp_dir
+        self._checkpoint_name = checkpoint
+        self.sample_rate = pp_hp.sr
+        self.wps = pp_hp.wps
+        self.midi_source = midi_source
+        self.audio_source = audio_source
+
+    @property
+    def checkpoint(self):
+        return torch.load(os.path.join(self.exp_dir, self._checkpoint_name))
+
+    def process_custom_midi(self, midi_path):
+        """inference.py:39-51: (pianoroll, onoff) transposed to (128, T)."""
+        pitch, velocity, start, end = read_midi_notes(midi_path)
+        pianoroll, onoff = notes_to_pianoroll(pitch, velocity, start, end, fs=self.wps)
+        return np.transpose(pianoroll, (1, 0)), np.transpose(onoff, (1, 0))
+
+    def process_custom_audio(self, audio):
+        """inference.py:54-55: whole-song log1p-power spectrogram."""
+        return process_spectrum_from_chunk(audio)
+
+    def griffinlim(self, spectrogram, audio_id=None, n_iter=300, window='hann', n_fft=2048, hop_length=256,
+                   verbose=False, random_state=None, init_phase=None):
+        """inference.py:105-110.  ``spectrogram`` is the model's log1p-power output, (1025, T).
+
+        magnitude = sqrt(expm1(clip(spectrogram, 0, 20))) is fused into the kernel that ingests the spectrogram;
+        then librosa.griffinlim(magnitude, n_iter, window='hann', win_length=n_fft, hop_length) semantics.
+        """
+        was_np = not isinstance(spectrogram, torch.Tensor)
+        device = _lib.require_cuda(None if was_np else spectrogram.device)
+        S = torch.from_numpy(np.ascontiguousarray(spectrogram, dtype=np.float32)).to(device) if was_np \
+            else spectrogram.to(torch.float32)
+        if S.dim() != 2 or S.shape[0] != features.N_BINS:
+            raise ValueError(f"spectrogram must be (1025, T); got {tuple(S.shape)}")
+        features._check_window(window, n_fft, n_fft)
+        T = int(S.shape[1])
+        if init_phase is None and isinstance(random_state, (int, np.integer)):
+            init_phase = np.random.RandomState(int(random_state)).rand(features.N_BINS, T)
+        ph = None
+        if init_phase is not None:
+            ph = init_phase if isinstance(init_phase, torch.Tensor) else \
+                torch.from_numpy(np.ascontiguousarray(init_phase, dtype=np.float32)).to(device)
+            ph = ph.to(torch.float32).contiguous()
+        b = features.ClipBatch.from_frames([T], int(hop_length), device=device)
+        y = features.griffinlim_batch(S.contiguous(), b, n_iter=n_iter, momentum=0.99, init_phase=ph, init="random",
+                                      seed=0 if audio_id is None else hash(str(audio_id)) & 0x7FFFFFFF,
+                                      layout=features.BIN_MAJOR, is_log1p_power=True)
+        b.close()
+        return y.cpu().numpy() if was_np else y

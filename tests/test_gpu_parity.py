@@ -1,0 +1,278 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through torch.ops.mst_b200 -> C ABI, against the NumPy oracle
+on the same seeded inputs.  Tolerances are BASELINE.json's: STFT / mel <= 1e-4 relative (float32), piano roll
+bit-exact, Griffin-Lim spectral convergence within 1e-3 of the oracle at equal iteration count."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import griffinlim as ogl, mel as omel, pianoroll as opr, preprocess as opp, stft as ostft
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.complex128 if np.iscomplexobj(a) else np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def rel_max(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def assert_close(a, b, tol=TOL):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert rel_l2(a, b) <= tol and rel_max(a, b) <= tol, (rel_l2(a, b), rel_max(a, b))
+
+
+@pytest.fixture(scope="module")
+def pkg(gpu):
+    import ml_music_style_transfer_b200 as p
+    return p
+
+
+def clip(seed, n, kind="piano"):
+    from ml_music_style_transfer_b200 import synth
+    if kind == "piano":
+        return synth.piano_clip(seed, n / 22050.0, 22050)[:n]
+    return synth.noise_clip(seed, n)
+
+
+# ---- P1: STFT ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("hop", [256, 512])
+@pytest.mark.parametrize("pad", ["reflect", "constant"])
+@pytest.mark.parametrize("n", [88200, 30001, 2049])
+def test_stft_complex(pkg, hop, pad, n):
+    y = clip(n, n, "noise" if n == 30001 else "piano")
+    D = pkg.features.stft(y, hop_length=hop, pad_mode=pad)
+    ref = ostft.stft(y, 2048, hop, pad_mode=pad)
+    assert D.dtype == np.complex64 and D.flags.f_contiguous
+    assert_close(D, ref)
+
+
+def test_stft_known_answers(pkg):
+    n = np.arange(8192)
+    D = pkg.features.stft(np.cos(2 * np.pi * 100 * n / 2048).astype(np.float32), hop_length=512)[:, 8]
+    assert abs(abs(D[100]) - 512.0) < 0.05 and abs(abs(D[99]) - 256.0) < 0.05 and np.abs(D[104:150]).max() < 0.05
+    D = pkg.features.stft(np.ones(8192, dtype=np.float32), hop_length=512)[:, 8]
+    assert abs(D[0].real - 1024.0) < 0.01 and abs(abs(D[1]) - 512.0) < 0.01 and np.abs(D[2:]).max() < 0.01
+    x = np.zeros(8192, dtype=np.float32)
+    x[4096 + 300] = 1.0
+    D = pkg.features.stft(x, hop_length=512)[:, 8]
+    assert np.allclose(np.abs(D), ostft.hann_window(2048)[1324], atol=1e-5)
+
+
+@pytest.mark.parametrize("out", ["magnitude", "power", "log1p_power"])
+def test_stft_epilogues(pkg, out):
+    y = clip(5, 44100)
+    ref = np.abs(ostft.stft(y, 2048, 256, out_dtype=np.complex128))
+    ref = {"magnitude": ref, "power": ref ** 2, "log1p_power": np.log1p(ref ** 2)}[out]
+    got = pkg.features.spectrogram(y, 256, out=out)
+    assert got.dtype == np.float32
+    assert_close(got, ref)
+
+
+def test_process_spectrum_from_chunk_dropin(pkg):
+    """preprocess.py:47-57 at the repo's own geometry (44.1 kHz, hop 256, 219 904-sample chunk -> 860 frames)."""
+    y = clip(11, 219904)
+    got = pkg.preprocess.process_spectrum_from_chunk(y)
+    ref = opp.process_spectrum_from_chunk(y)
+    assert got.shape == (1025, 860) and got.dtype == np.float32 and got.flags.f_contiguous
+    assert_close(got, ref.astype(np.float64))
+
+
+def test_process_audio_into_chunks_dropin(pkg):
+    """preprocess.py:60-77: overlapping chunks, each reflect-padded independently, C-contiguous stack."""
+    n = 2 * 131072 + 219904
+    y = clip(12, n, "noise")
+    got = pkg.preprocess.process_audio_into_chunks(y, "cuba", 2240, 3)
+    ref = opp.process_audio_into_chunks(y, "cuba", 2240, 3)
+    assert got.shape == (3, 1025, 860) and got.flags.c_contiguous
+    assert_close(got, ref.astype(np.float64))
+    with pytest.raises(ValueError):
+        pkg.preprocess.process_audio_into_chunks(y[:300000], "cuba", 2240, 3)
+
+
+def test_stft_ragged_batch_device_tensors(pkg, gpu):
+    """Ragged, overlapping clips in one launch; CUDA tensor in -> CUDA tensor out; both layouts."""
+    F = pkg.features
+    y = clip(13, 120000, "noise")
+    offs = np.array([0, 1000, 50001, 90000], dtype=np.int64)
+    lens = np.array([40000, 2049, 33333, 30000], dtype=np.int64)
+    a = torch.from_numpy(y).to(gpu)
+    b = F.ClipBatch.from_clips(offs, lens, 512, device=gpu)
+    fm = F.stft_batch(a, b, "log1p_power", F.FRAME_MAJOR).view(-1, 1025).cpu().numpy()
+    bm = F.stft_batch(a, b, "log1p_power", F.BIN_MAJOR).cpu().numpy()
+    f0 = 0
+    for o, l in zip(offs, lens):
+        ref = np.log1p(np.abs(ostft.stft(y[o:o + l], 2048, 512, out_dtype=np.complex128)) ** 2)
+        T = ref.shape[1]
+        assert_close(fm[f0:f0 + T].T, ref)
+        assert_close(bm[f0 * 1025:(f0 + T) * 1025].reshape(1025, T), ref)
+        f0 += T
+    assert f0 == b.total_frames
+
+
+# ---- P2: mel ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("sr,hop", [(22050, 512), (44100, 256)])
+def test_melspectrogram_and_logmel(pkg, sr, hop):
+    y = clip(21, 66150)
+    ref = omel.melspectrogram(y, sr, 2048, hop)
+    got = pkg.features.melspectrogram(y=y, sr=sr, n_fft=2048, hop_length=hop)
+    assert got.shape == ref.shape == (128, 1 + len(y) // hop) and got.dtype == np.float32
+    assert_close(got, ref.astype(np.float64))
+    assert_close(pkg.features.logmel(y, sr=sr, hop_length=hop), np.log1p(ref.astype(np.float64)))
+
+
+def test_mel_frame_major_batch(pkg, gpu):
+    F = pkg.features
+    y = clip(22, 4 * 88200, "noise")
+    a = torch.from_numpy(y).to(gpu)
+    b = F.ClipBatch.uniform(4, 88200, 512, device=gpu)
+    plan = F.MelPlan.get(22050, device=gpu)
+    got = F.melspectrogram_batch(a, b, plan, log1p=True, layout=F.FRAME_MAJOR).view(4, 173, 128).cpu().numpy()
+    for c in range(4):
+        assert_close(got[c].T, omel.logmel(y[c * 88200:(c + 1) * 88200], 22050, 2048, 512).astype(np.float64))
+
+
+# ---- P3: piano roll (bit-exact) -------------------------------------------------------------
+def test_pianoroll_known_answer(pkg):
+    roll, onoff = pkg.preprocess.notes_to_pianoroll([60, 60, 64, 21], [100, 90, 80, 1], [0, 0.5, 0.25, 0.999],
+                                                    [0.5, 1.0, 0.2501, 2.0])
+    assert roll.shape == (344, 128) and roll.dtype == np.float64
+    on = np.nonzero(onoff[:, 60])[0]
+    assert list(on) == [0, 172] and list(onoff[on, 60]) == [1.0, -1.0]
+    assert roll[:, 64].sum() == 0
+    # int(0.29*100) == 28: truncation of the float64 product
+    r2, _ = pkg.preprocess.notes_to_pianoroll([50], [10], [0.29], [0.5], fs=100)
+    assert r2[28, 50] == 1 and r2[27, 50] == 0
+    vs = pkg.pianoroll.get_piano_roll([60, 60, 64, 21], [100, 90, 80, 1], [0, 0.5, 0.25, 0.999], [0.5, 1.0, 0.2501, 2.0], 172)
+    assert np.array_equal(vs, opr.get_piano_roll([60, 60, 64, 21], [100, 90, 80, 1], [0, 0.5, 0.25, 0.999], [0.5, 1.0, 0.2501, 2.0], 172))
+
+
+@pytest.mark.parametrize("fs,sr,pitch_lo,n_keys", [(250, 22050, 21, 88), (172, 44100, 0, 128)])
+def test_pianoroll_batch_bit_exact(pkg, gpu, fs, sr, pitch_lo, n_keys):
+    from ml_music_style_transfer_b200 import synth
+    P = pkg.pianoroll
+    pieces = [synth.midi_piece(i, seconds=4.0 + i) for i in range(5)]
+    pieces.append((np.array([60], np.int32), np.array([5], np.int32), np.array([0.0]), np.array([0.001])))  # empty roll
+    nb = P.NoteBatch.from_pieces(pieces, device=gpu)
+    roll, onoff, row_off, velsum = P.rasterize(nb, fs, want_velsum=True)
+    ro = row_off.cpu().numpy()
+    n_samp = [int(sr * 1.5) + 7 * i for i in range(len(pieces))]
+    up, so = P.upsample(roll, row_off, n_samp, fs, sr, pitch_lo, n_keys, torch.int8)
+    up_oo, _ = P.upsample(onoff, row_off, n_samp, fs, sr, pitch_lo, n_keys, torch.float32)
+    up, up_oo = up.cpu().numpy(), up_oo.cpu().numpy()
+    for i, (p, v, s, e) in enumerate(pieces):
+        ref_v = opr.get_piano_roll(p, v, s, e, fs)
+        ref_r, ref_o = opr.binarize_and_onoff(ref_v)
+        T = ref_v.shape[1]
+        assert ro[i + 1] - ro[i] == T
+        assert np.array_equal(velsum[ro[i]:ro[i + 1]].cpu().numpy().T, ref_v)
+        assert np.array_equal(roll[ro[i]:ro[i + 1]].cpu().numpy(), ref_r)
+        assert np.array_equal(onoff[ro[i]:ro[i + 1]].cpu().numpy(), ref_o)
+        N = n_samp[i]
+        blk = up[n_keys * so[i]:n_keys * so[i + 1]].reshape(n_keys, N)
+        assert np.array_equal(blk, opr.upsample_to_audio_rate(ref_r, fs, sr, N, pitch_lo, n_keys, np.int8))
+        blk = up_oo[n_keys * so[i]:n_keys * so[i + 1]].reshape(n_keys, N)
+        assert np.array_equal(blk, opr.upsample_to_audio_rate(ref_o, fs, sr, N, pitch_lo, n_keys, np.float32))
+
+
+def test_process_pianoroll_into_chunks_dropin(pkg):
+    from ml_music_style_transfer_b200 import synth
+    p, v, s, e = synth.midi_piece(3, seconds=14.0)
+    roll, onoff = pkg.preprocess.notes_to_pianoroll(p, v, s, e)
+    ref_r, ref_o = opp.midi_notes_to_pianoroll(p, v, s, e)
+    assert np.array_equal(roll, ref_r) and np.array_equal(onoff, ref_o)
+    n = pkg.preprocess.get_num_song_chunks(roll)
+    assert n == opp.get_num_song_chunks(ref_r) and n >= 2
+    a, b = pkg.preprocess.process_pianoroll_into_chunks(roll, onoff, 1, n)
+    ra, rb = opp.process_pianoroll_into_chunks(ref_r, ref_o, 1, n)
+    assert a.dtype == np.float64 and np.array_equal(a, ra) and np.array_equal(b, rb)
+
+
+def test_load_midi_dropin(pkg, tmp_path):
+    from ml_music_style_transfer_b200 import midi, synth
+    p, v, s, e = synth.midi_piece(4, seconds=8.0)
+    midi.write_midi_notes(str(tmp_path / "2240_x_mixcraft.mid"), p, v, s, e)
+    roll, onoff = pkg.preprocess.load_midi(str(tmp_path), 2240)
+    rp, rv, rs, re_ = midi.read_midi_notes(str(tmp_path / "2240_x_mixcraft.mid"))
+    ref_r, ref_o = opp.midi_notes_to_pianoroll(rp, rv, rs, re_)
+    assert np.array_equal(roll, ref_r) and np.array_equal(onoff, ref_o)
+    with pytest.raises(ValueError):
+        pkg.preprocess.load_midi(str(tmp_path), 9999)
+
+
+# ---- P4: Griffin-Lim ------------------------------------------------------------------------
+def _sc(S, y, hop):
+    return ogl.spectral_convergence(S, y, hop)
+
+
+@pytest.mark.parametrize("hop,n_iter,mom", [(512, 32, 0.99), (256, 32, 0.99), (512, 16, 0.0)])
+def test_griffinlim_spectral_convergence(pkg, hop, n_iter, mom):
+    y = clip(31, 44100)
+    S = np.abs(ostft.stft(y, 2048, hop)).astype(np.float32)
+    u = ogl.random_phase(S.shape, 0)
+    ref = ogl.griffinlim(S, n_iter, hop, momentum=mom, init_phase=u)
+    got = pkg.features.griffinlim(S, n_iter=n_iter, hop_length=hop, momentum=mom, init_phase=u)
+    assert got.shape == ref.shape == (hop * (S.shape[1] - 1),) and got.dtype == np.float32
+    sc_ref, sc_got = _sc(S, ref, hop), _sc(S, got, hop)
+    assert abs(sc_ref - sc_got) <= 1e-3, (sc_ref, sc_got)
+    assert sc_got < 0.5
+
+
+def test_griffinlim_early_iterations_match_waveform(pkg):
+    """Before the chaotic phase dynamics amplify float32 rounding, the waveform itself must agree."""
+    y = clip(32, 30000)
+    S = np.abs(ostft.stft(y, 2048, 512)).astype(np.float32)
+    u = ogl.random_phase(S.shape, 1)
+    for n_iter in (0, 1, 2):
+        ref = ogl.griffinlim(S, n_iter, 512, init_phase=u)
+        got = pkg.features.griffinlim(S, n_iter=n_iter, hop_length=512, init_phase=u)
+        assert rel_l2(got, ref.astype(np.float64)) < 2e-4, (n_iter, rel_l2(got, ref.astype(np.float64)))
+    ref = ogl.griffinlim(S, 2, 512, init_phase=None)
+    got = pkg.features.griffinlim(S, n_iter=2, hop_length=512, init=None)
+    assert rel_l2(got, ref.astype(np.float64)) < 2e-4
+
+
+def test_audiosynthesizer_griffinlim_dropin(pkg):
+    """inference.py:105-110: log1p-power in, sqrt(expm1(clip)) fused, hop 256."""
+    y = clip(33, 30000)
+    spec = opp.process_spectrum_from_chunk(y)  # (1025, T) log1p power, what the model emits
+    mag = ogl.logpower_to_magnitude(spec)
+    u = ogl.random_phase(spec.shape, 5)
+    synth_ = pkg.inference.AudioSynthesizer(None, None, None, None)
+    got = synth_.griffinlim(spec, "a", n_iter=24, init_phase=u)
+    ref = ogl.griffinlim(mag, 24, 256, init_phase=u)
+    assert got.shape == ref.shape
+    assert abs(_sc(mag, ref, 256) - _sc(mag, got, 256)) <= 1e-3
+    # device RNG path: different phase draw, same convergence behaviour
+    got2 = synth_.griffinlim(spec, "b", n_iter=24)
+    assert _sc(mag, got2, 256) < 1.5 * _sc(mag, ref, 256) + 0.05
+
+
+def test_griffinlim_batch_full_size_round_trip(pkg, gpu):
+    """Size-independent property at scale: with the TRUE phase as initial phase and n_iter=0 the synthesis launch is
+    istft(stft(y)) and must return y (COLA); a ragged batch exercises the packed layout."""
+    F = pkg.features
+    frames = [173, 200, 57, 173]
+    hop = 512
+    lens = [hop * (t - 1) for t in frames]
+    y = clip(34, sum(lens), "noise")
+    a = torch.from_numpy(y).to(gpu)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    b = F.ClipBatch.from_clips(offs, lens, hop, device=gpu)
+    D = F.stft_batch(a, b, "complex")  # (total_frames, 1025) complex64, frame-major
+    S = D.abs().contiguous()
+    ph = (torch.angle(D) / (2 * np.pi)) % 1.0
+    gb = F.ClipBatch.from_frames(frames, hop, device=gpu)
+    out = F.griffinlim_batch(S, gb, n_iter=0, init_phase=ph.float().contiguous(), layout=F.FRAME_MAJOR).cpu().numpy()
+    o = 0
+    for l in lens:
+        seg, ref = out[o:o + l], y[o:o + l]
+        assert np.abs(seg - ref)[1024:-1024].max() < 5e-5
+        o += l
+    # and a few iterations from there must keep the consistent spectrogram (fixed point of the projection)
+    out2 = F.griffinlim_batch(S, gb, n_iter=3, init_phase=ph.float().contiguous(), layout=F.FRAME_MAJOR).cpu().numpy()
+    assert np.abs(out2 - y)[2048:l - 2048].max() < 5e-3

@@ -1,0 +1,221 @@
+"""CPU suite (-m "not gpu"): pins the oracle against independent implementations (golden fixtures made by
+tests/golden/make_golden.py) and closed-form known answers; checks host logic and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import griffinlim as ogl, mel as omel, pianoroll as opr, preprocess as opp, stft as ostft
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+# ---- STFT / iSTFT ------------------------------------------------------------------------------
+@pytest.mark.parametrize("hop", [256, 512])
+@pytest.mark.parametrize("pad", ["reflect", "constant"])
+def test_stft_matches_torch_golden(hop, pad):
+    g = np.load(os.path.join(GOLD, "stft_torch.npz"))
+    D = ostft.stft(g["y"], 2048, hop, pad_mode=pad)
+    ref = g[f"stft_{hop}_{pad}"]
+    assert D.shape == ref.shape == (1025, 1 + 6000 // hop)
+    assert D.dtype == np.complex64 and D.flags.f_contiguous
+    assert relerr(D, ref) < 2e-7
+
+
+@pytest.mark.parametrize("hop", [256, 512])
+def test_istft_matches_torch_golden(hop):
+    g = np.load(os.path.join(GOLD, "stft_torch.npz"))
+    y = ostft.istft(g[f"stft_{hop}_reflect"], hop)
+    ref = g[f"istft_{hop}"]
+    assert y.shape == ref.shape == (hop * (6000 // hop),)
+    assert np.abs(y - ref).max() < 2e-6
+
+
+def test_stft_known_answers():
+    n = np.arange(8192)
+    # cosine on a bin centre: |X[k0]| = N/4 * 2 = 512 (Hann sum = N/2, half per sideband), neighbours half of that
+    k0 = 100
+    D = ostft.stft(np.cos(2 * np.pi * k0 * n / 2048).astype(np.float32), 2048, 512, out_dtype=np.complex128)
+    mid = D[:, 8]
+    assert abs(abs(mid[k0]) - 512.0) < 1e-3
+    assert abs(abs(mid[k0 - 1]) - 256.0) < 1e-3 and abs(abs(mid[k0 + 1]) - 256.0) < 1e-3
+    assert np.abs(mid[k0 + 3:k0 + 50]).max() < 1e-3
+    # DC: only bins 0 and 1
+    D = ostft.stft(np.ones(8192, dtype=np.float32), 2048, 512, out_dtype=np.complex128)[:, 8]
+    assert abs(D[0].real - 1024.0) < 1e-9 and abs(abs(D[1]) - 512.0) < 1e-9 and np.abs(D[2:]).max() < 1e-9
+    # unit impulse at frame position n0: flat magnitude w[n0]
+    x = np.zeros(8192, dtype=np.float32)
+    x[4096 + 300] = 1.0
+    D = ostft.stft(x, 2048, 512, out_dtype=np.complex128)[:, 8]  # frame 8 starts at padded 4096 -> sample 3072
+    w = ostft.hann_window(2048)[4096 + 300 - 3072]
+    assert np.allclose(np.abs(D), w, atol=1e-12)
+
+
+def test_cola_round_trip():
+    y = (0.1 * np.random.default_rng(3).standard_normal(20000)).astype(np.float32)
+    for hop in (256, 512):
+        r = ostft.istft(ostft.stft(y, 2048, hop), hop)
+        assert np.abs(r - y[:len(r)])[1024:-1024].max() < 1e-6
+
+
+def test_chunk_geometry():
+    hp = opp.hyperparams()
+    assert hp.wps == 172 and hp.spc * hp.wps == 860
+    n = (hp.spc * hp.wps - 1) * hp.ws
+    assert n == 219904 and ostft.frame_count(n, hp.ws) == 860 and hp.ws * hp.stride == 131072
+    audio = (0.1 * np.random.default_rng(0).standard_normal(131072 + 219904)).astype(np.float32)
+    out = opp.process_audio_into_chunks(audio, "s", 1, 2)
+    assert out.shape == (2, 1025, 860) and out.dtype == np.float32
+
+
+# ---- mel ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sr,nnz", [(22050, 2018), (44100, 2014)])
+def test_mel_filterbank_matches_torchaudio_golden(sr, nnz):
+    ref = np.load(os.path.join(GOLD, "mel_torchaudio.npz"))[f"fb_{sr}"]
+    W = omel.mel_filterbank(sr, 2048, 128)
+    assert W.shape == (128, 1025) and W.dtype == np.float32
+    assert int((W != 0).sum()) == nnz
+    assert (W >= 0).all()
+    assert np.abs(W - ref).max() / np.abs(ref).max() < 1e-5
+    # banded: non-zeros of every row are contiguous
+    for row in W:
+        idx = np.nonzero(row)[0]
+        assert len(idx) >= 2 and idx[-1] - idx[0] + 1 == len(idx)
+
+
+def test_c_abi_mel_filterbank_is_bit_exact_with_oracle(built_libs):
+    lib = ctypes.CDLL(built_libs[0])
+    for sr in (22050, 44100):
+        W = np.zeros((128, 1025), dtype=np.float32)
+        rc = lib.mst_mel_filterbank_f32(sr, 2048, 128, ctypes.c_double(0.0), ctypes.c_double(0.0),
+                                        W.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        assert np.array_equal(W, omel.mel_filterbank(sr, 2048, 128))
+
+
+# ---- piano roll --------------------------------------------------------------------------------
+def test_pianoroll_known_answer():
+    roll = opr.get_piano_roll([60, 60, 64, 21], [100, 90, 80, 1], [0, 0.5, 0.25, 0.999], [0.5, 1.0, 0.2501, 2.0], 172)
+    assert roll.shape == (128, 344)
+    pr, oo = opr.binarize_and_onoff(roll)
+    on = np.nonzero(oo[:, 60])[0]
+    assert list(on) == [0, 172] and list(oo[on, 60]) == [1.0, -1.0]  # legato merge: one onset, one offset
+    assert pr[:, 64].sum() == 0  # zero-length note after truncation
+    assert roll[60, 85] == 100 and roll[60, 86] == 90  # int(0.5*172) == 86
+    assert int(0.29 * 100) == 28  # the float64 truncation case the device code must reproduce
+    assert np.array_equal(oo, opr.onoff_reference_loop(pr))
+
+
+def test_onoff_loop_equals_difference_random():
+    from ml_music_style_transfer_b200 import synth
+    p, v, s, e = synth.midi_piece(0, seconds=6.0)
+    pr, oo = opr.binarize_and_onoff(opr.get_piano_roll(p, v, s, e, 172))
+    assert np.array_equal(oo, opr.onoff_reference_loop(pr))
+    assert set(np.unique(oo)) <= {-1.0, 0.0, 1.0}
+
+
+def test_upsample_definition():
+    x = np.zeros((10, 128), dtype=np.int8)
+    x[3, 21] = 1
+    x[9, 108] = -1
+    up = opr.upsample_to_audio_rate(x, 250, 22050, 1000)
+    assert up.shape == (88, 1000)
+    cols = (np.arange(1000) * 250) // 22050
+    assert np.array_equal(up[0], (cols == 3).astype(np.int8))
+    assert np.array_equal(up[87], -(cols == 9).astype(np.int8))
+    assert up[:, cols >= 10].sum() == 0
+
+
+def test_num_song_chunks():
+    assert opr.get_num_song_chunks(5160) == (5160 - 860) // 512 - int(0.1 * ((5160 - 860) // 512))
+    assert opr.get_num_song_chunks(10 ** 6) == 100
+
+
+# ---- Griffin-Lim -------------------------------------------------------------------------------
+@pytest.mark.parametrize("mom", [0.99, 0.0])
+def test_griffinlim_matches_torchaudio_golden(mom):
+    g = np.load(os.path.join(GOLD, "griffinlim_torchaudio.npz"))
+    y = ogl.griffinlim(g["mag"], 8, 512, momentum=mom, init_phase=None)
+    ref = g[f"y_iter8_mom{mom}"]
+    assert y.shape == (512 * (g["mag"].shape[1] - 1),)
+    assert np.abs(y - ref[:len(y)]).max() < 2e-4 * np.abs(ref).max()
+
+
+def test_griffinlim_converges_and_inverse_map():
+    from ml_music_style_transfer_b200 import synth
+    y = synth.piano_clip(1, 1.0, 22050)
+    S = np.abs(ostft.stft(y, 2048, 512)).astype(np.float32)
+    _, hist = ogl.griffinlim(S, 16, 512, init_phase=ogl.random_phase(S.shape, 0), return_history=True)
+    assert hist[-1] < hist[0] and hist[-1] < 0.5
+    p = (S ** 2)
+    back = ogl.logpower_to_magnitude(np.log1p(p))
+    assert np.allclose(back, S, rtol=2e-3, atol=1e-4)
+
+
+# ---- host logic --------------------------------------------------------------------------------
+def test_header_symbols_exported(built_libs):
+    hdr = open(os.path.join(ROOT, "include", "mst_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(mst_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    lib = ctypes.CDLL(built_libs[0])
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mst_b200.h but not exported"
+    lib.mst_last_error.restype = ctypes.c_char_p
+    assert lib.mst_version() >= 100
+
+
+def test_torch_ops_load_and_refuse_cpu(built_libs):
+    import torch
+    import ml_music_style_transfer_b200 as pkg
+    ops = pkg._lib.ops()
+    W = ops.mel_filterbank(22050, 2048, 128, 0.0, 0.0)
+    assert tuple(W.shape) == (128, 1025)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        ops.stft(torch.zeros(4096), 0, 3, 0)  # no CPU kernel is registered
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            pkg.preprocess.process_spectrum_from_chunk(np.zeros(4096, dtype=np.float32))
+
+
+def test_batch_argument_errors(built_libs):
+    lib = ctypes.CDLL(built_libs[0])
+    lib.mst_last_error.restype = ctypes.c_char_p
+    out = ctypes.c_void_p()
+    off = (ctypes.c_int64 * 1)(0)
+    ln = (ctypes.c_int64 * 1)(4096)
+    assert lib.mst_batch_create(1, off, ln, 1024, 256, 0, ctypes.byref(out)) == -2  # MST_ERR_UNSUPPORTED
+    assert b"2048" in lib.mst_last_error()
+    ln[0] = 1000
+    assert lib.mst_batch_create(1, off, ln, 2048, 256, 0, ctypes.byref(out)) == -1  # too short for reflect
+
+
+def test_midi_reader_round_trip(tmp_path):
+    from ml_music_style_transfer_b200 import midi
+    p = [60, 60, 64, 72]
+    v = [100, 90, 80, 1]
+    s = [0.0, 0.5, 0.25, 1.0]
+    e = [0.5, 1.0, 0.75, 2.0]
+    path = str(tmp_path / "x.mid")
+    midi.write_midi_notes(path, p, v, s, e)
+    rp, rv, rs, re_ = midi.read_midi_notes(path)
+    order = np.lexsort((rp, rs))
+    assert list(rp[order]) == [60, 64, 60, 72]
+    assert np.allclose(np.sort(rs), np.sort(s)) and np.allclose(np.sort(re_), np.sort(e))
+
+
+def test_shard_ranges_partition():
+    from ml_music_style_transfer_b200 import sharding
+    for n in (0, 1, 7, 16384, 4080):
+        for w in (1, 2, 4, 8):
+            r = [sharding.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
