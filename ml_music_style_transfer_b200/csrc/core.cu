@@ -36,27 +36,33 @@ int get_tables(Tables* out) {
   if (dev < 0 || dev >= 64) return fail(MST_ERR_INVALID, "device index %d out of range", dev);
   std::lock_guard<std::mutex> lock(g_table_mutex);
   if (!g_tables_ready[dev]) {
-    std::vector<float2> tw1(1024), tw2(1024);
-    std::vector<float> win(kNfft);
+    std::vector<float2> tw1(1024), twp(kTwpCount, make_float2(0.f, 0.f));
+    std::vector<float> win(kNfft), wsyn(kNfft);
     const double two_pi = 6.283185307179586476925286766559;
     for (int k1 = 0; k1 < 32; ++k1)
       for (int n2 = 0; n2 < 32; ++n2) {
         const double a = -two_pi * (double)(k1 * n2) / 1024.0;
         tw1[k1 * 32 + n2] = make_float2((float)cos(a), (float)sin(a));
       }
-    for (int k = 0; k < 1024; ++k) {
-      const double a = -two_pi * (double)k / 2048.0;
-      tw2[k] = make_float2((float)cos(a), (float)sin(a));
+    for (int k = 0; k <= 512; ++k) {
+      const double a = -two_pi * (double)k / 2048.0;  // w = (cos a, sin a); -0.5i*w = (0.5 sin a, -0.5 cos a)
+      twp[k] = make_float2((float)(0.5 * sin(a)), (float)(-0.5 * cos(a)));
     }
-    for (int n = 0; n < kNfft; ++n) win[n] = (float)(0.5 - 0.5 * cos(two_pi * (double)n / (double)kNfft));
+    for (int n = 0; n < kNfft; ++n) {
+      win[n] = (float)(0.5 - 0.5 * cos(two_pi * (double)n / (double)kNfft));
+      wsyn[n] = win[n] * (1.0f / 1024.0f);
+    }
+    const size_t bytes = 8192 + sizeof(float2) * kTwpCount + 8192 + 8192;
     char* d = nullptr;
-    MST_CUDA_OK(cudaMalloc(&d, kTableBytes));
+    MST_CUDA_OK(cudaMalloc(&d, bytes));
     MST_CUDA_OK(cudaMemcpy(d, tw1.data(), 8192, cudaMemcpyHostToDevice));
-    MST_CUDA_OK(cudaMemcpy(d + 8192, tw2.data(), 8192, cudaMemcpyHostToDevice));
-    MST_CUDA_OK(cudaMemcpy(d + 16384, win.data(), 8192, cudaMemcpyHostToDevice));
+    MST_CUDA_OK(cudaMemcpy(d + 8192, twp.data(), sizeof(float2) * kTwpCount, cudaMemcpyHostToDevice));
+    MST_CUDA_OK(cudaMemcpy(d + 8192 + sizeof(float2) * kTwpCount, win.data(), 8192, cudaMemcpyHostToDevice));
+    MST_CUDA_OK(cudaMemcpy(d + 16384 + sizeof(float2) * kTwpCount, wsyn.data(), 8192, cudaMemcpyHostToDevice));
     g_tables[dev].tw1024 = reinterpret_cast<const float2*>(d);
-    g_tables[dev].tw2048 = reinterpret_cast<const float2*>(d + 8192);
-    g_tables[dev].window = reinterpret_cast<const float*>(d + 16384);
+    g_tables[dev].twp = reinterpret_cast<const float2*>(d + 8192);
+    g_tables[dev].window = reinterpret_cast<const float*>(d + 8192 + sizeof(float2) * kTwpCount);
+    g_tables[dev].wsyn = reinterpret_cast<const float*>(d + 16384 + sizeof(float2) * kTwpCount);
     g_tables_ready[dev] = true;
   }
   *out = g_tables[dev];
@@ -198,7 +204,27 @@ int mst_batch_create_from_frames(int n_clips, const int64_t* h_frames, int n_fft
       }
       wss_off[c] = found;
     }
-    if (cudaMalloc(&b->d_inv_wss, sizeof(float) * env.size()) != cudaSuccess ||
+    // Interior frames (all n_fft/hop overlapping neighbours present) see an envelope that is periodic in hop; fold it
+    // into the analysis window once.  Computed like the envelopes above (float32 accumulation in frame order).
+    std::vector<float> wq(kNfft, 0.0f);
+    {
+      const int q = (kNfft - 1) / hop;
+      const int32_t Tq = 2 * q + 1;  // smallest clip with one interior frame (frame q)
+      std::vector<float> x((size_t)kNfft + (size_t)hop * (Tq - 1), 0.0f);
+      for (int32_t t = 0; t < Tq; ++t) {
+        float* p = x.data() + (int64_t)t * hop;
+        for (int j = 0; j < kNfft; ++j) p[j] = (float)((double)p[j] + wsq[j]);
+      }
+      const float tiny = 1.17549435e-38f;
+      for (int j = 0; j < kNfft; ++j) {
+        const float e = x[(size_t)q * hop + j];
+        const float w = (float)(0.5 - 0.5 * cos(two_pi * (double)j / (double)kNfft));
+        wq[j] = w * (e > tiny ? 1.0f / e : 1.0f);
+      }
+    }
+    if (cudaMalloc(&b->d_wq, sizeof(float) * kNfft) != cudaSuccess ||
+        cudaMemcpy(b->d_wq, wq.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMalloc(&b->d_inv_wss, sizeof(float) * env.size()) != cudaSuccess ||
         cudaMemcpy(b->d_inv_wss, env.data(), sizeof(float) * env.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMalloc(&b->d_wss_offset, sizeof(int64_t) * (size_t)n_clips) != cudaSuccess ||
         cudaMemcpy(b->d_wss_offset, wss_off.data(), sizeof(int64_t) * (size_t)n_clips, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -215,6 +241,7 @@ void mst_batch_destroy(mst_batch_t* b) {
   if (b->d_clips) cudaFree(b->d_clips);
   if (b->d_tile_clip) cudaFree(b->d_tile_clip);
   if (b->d_inv_wss) cudaFree(b->d_inv_wss);
+  if (b->d_wq) cudaFree(b->d_wq);
   if (b->d_wss_offset) cudaFree(b->d_wss_offset);
   delete[] b->h_clips;
   delete b;

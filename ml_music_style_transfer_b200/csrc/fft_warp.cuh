@@ -5,7 +5,7 @@
 // W_1024^(k1*n2) twiddles, a 32x32 transpose through a padded per-warp shared-memory tile, and pass 2
 // (another in-register FFT-32).  Output element k = l + 32*r sits in register slot BR5(r) of lane l,
 // i.e. the output layout equals the input layout, so forward and inverse chain without reshuffles.
-// The real-FFT split / merge butterflies exchange bin k with bin 1024-k through the same scratch tile.
+// The real-FFT split / merge butterflies exchange bin k with bin 1024-k by warp shuffle (mirror layout below).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -66,8 +66,10 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
 
 // 1024-point complex FFT across one warp.  `scratch` is this warp's 32x33 float2 tile,
 // `tw` the shared-memory table exp(-2*pi*i*k1*n2/1024) laid out [k1][n2].
+// fft1024_front leaves the transposed intermediate in v[] and the scratch tile FREE (callers may start asynchronous
+// copies into it); the transform is completed by fft32<SIGN>(v).
 template <int SIGN>
-__device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* scratch, const float2* tw, int lane) {
+__device__ __forceinline__ void fft1024_front(float2 (&v)[32], float2* scratch, const float2* tw, int lane) {
   fft32<SIGN>(v);
 #pragma unroll
   for (int k1 = 0; k1 < 32; ++k1) {
@@ -83,70 +85,121 @@ __device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* scratch, c
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = scratch[lane * 33 + j];
   __syncwarp();
+}
+
+template <int SIGN>
+__device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* scratch, const float2* tw, int lane) {
+  fft1024_front<SIGN>(v, scratch, tw, lane);
   fft32<SIGN>(v);
 }
 
-// Forward real FFT of a 2048-sample frame held as z[m] = x[2m] + i*x[2m+1], m = 32*r + lane in v[r].
-// On return X[k], k = lane + 32*r, is in x[r] (natural register order); *nyq = X[1024].x (valid on lane 0).
-// The split butterfly pairs bin k with bin 1024-k; the pair is exchanged through the warp's scratch tile
-// (linear [k] layout, mirrored read) so that no second register copy of the spectrum stays live.
-__device__ __forceinline__ void rfft2048_warp(float2 (&v)[32], float2 (&x)[32], float* nyq, float2* scratch,
-                                              const float2* tw1024, const float2* tw2048, int lane) {
-  fft1024_warp<-1>(v, scratch, tw1024, lane);
-#pragma unroll
-  for (int r = 0; r < 32; ++r) scratch[r * 32 + lane] = v[br5(r)];
-  __syncwarp();
-  *nyq = v[0].x - v[0].y;  // Z[0] lives in register slot br5(0) = 0 of lane 0
-#pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    const float2 z = v[br5(r)];
-    const float2 p = scratch[(1024 - (lane + 32 * r)) & 1023];
-    const float2 w = tw2048[lane + 32 * r];
-    const float er = 0.5f * (z.x + p.x), ei = 0.5f * (z.y - p.y);
-    const float orr = 0.5f * (z.y + p.y), oi = -0.5f * (z.x - p.x);
-    x[r] = make_float2(er + fmaf(w.x, orr, -w.y * oi), ei + fmaf(w.x, oi, w.y * orr));
-  }
-  __syncwarp();
+// ---- real <-> half-length complex conversion ("mirror layout") ------------------------------------------------
+// The split / merge butterflies of a real FFT pair bin k with bin 1024-k.  After the complex FFT lane l holds
+// Z[l + 32*r]; bin 1024-k of its bins k = l + 32*r, r < 16, sits in lane (32-l)&31, register 31-r.  One warp shuffle
+// per pair moves it over, after which lane l owns BOTH bins of 16 pairs and one complex multiply serves two outputs.
+// Resulting register layout of a 1025-bin spectrum ("mirror layout"), j = 0..31:
+//     j <  16 : bin l + 32*j
+//     j >= 16 : bin (32 - l) + 32*j          (lane 0: bin 32*(j+1), so j = 31 is the Nyquist bin 1024)
+//     lane 0 additionally holds bin 512 in a separate register ("mid").
+// All elementwise spectrum work (epilogues, Griffin-Lim re-projection) runs in this layout; global accesses stay
+// coalesced because consecutive lanes still touch consecutive (ascending or descending) bins.
+// kb = mirror_base(lane) is computed once per thread so that every bin index is (lane | kb) + compile-time constant.
+__device__ __forceinline__ int mirror_base(int lane) { return lane == 0 ? 32 : 32 - lane; }
+__device__ __forceinline__ int mirror_bin(int lane, int kb, int j) { return j < 16 ? lane + 32 * j : kb + 32 * j; }
+
+// One pair butterfly.  z = value at bin k, p = value at bin 1024-k, w = -0.5i*exp(-2*pi*i*k/2048) (conjugated by the
+// caller for the inverse direction).  Returns out_k = 0.5*(z + conj p) + w*(z - conj p) and
+// out_m = conj(0.5*(z + conj p) - w*(z - conj p)).
+__device__ __forceinline__ void pair_butterfly(float2 z, float2 p, float2 w, float2& out_k, float2& out_m) {
+  const float sx = z.x + p.x, sy = z.y - p.y;
+  const float dx = z.x - p.x, dy = z.y + p.y;
+  const float tx = fmaf(w.x, dx, -w.y * dy), ty = fmaf(w.x, dy, w.y * dx);
+  out_k = make_float2(fmaf(0.5f, sx, tx), fmaf(0.5f, sy, ty));
+  out_m = make_float2(fmaf(0.5f, sx, -tx), fmaf(-0.5f, sy, ty));
 }
 
-// Inverse real FFT: Y[k], k = lane + 32*r in y[r] (natural order) plus Y[1024].x in `nyq` (lane 0).
-// Returns z[m] = x[2m] + i*x[2m+1], m = lane + 32*r, UNSCALED by 1/1024, in v[br5(r)].
-// Imaginary parts of the DC and Nyquist bins are ignored, as pocketfft's c2r does.
-__device__ __forceinline__ void irfft2048_warp(float2 (&y)[32], float nyq, float2 (&v)[32], float2* scratch,
-                                               const float2* tw1024, const float2* tw2048, int lane) {
+// Forward real FFT of a 2048-sample frame held as z[m] = x[2m] + i*x[2m+1], m = 32*r + lane in v[r].
+// Result: spectrum in mirror layout in o[0..31], bin 512 in *mid (lane 0 only).
+// twp[k], k = 0..512: -0.5i * exp(-2*pi*i*k/2048).
+__device__ __forceinline__ void rfft_split(float2 (&v)[32], float2 (&o)[32], float2* mid, const float2* twp, int lane) {
+  const int src = (32 - lane) & 31;
 #pragma unroll
-  for (int r = 0; r < 32; ++r) scratch[r * 32 + lane] = y[r];
-  __syncwarp();
-#pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    const float2 a = y[r];
-    const float2 p = scratch[(1024 - (lane + 32 * r)) & 1023];
-    const float2 w = tw2048[lane + 32 * r];  // exp(-i*theta); the merge needs exp(+i*theta) = conj(w)
-    const float er = 0.5f * (a.x + p.x), ei = 0.5f * (a.y - p.y);
-    const float dr = 0.5f * (a.x - p.x), di = 0.5f * (a.y + p.y);
-    const float opr = fmaf(dr, w.x, di * w.y), opi = fmaf(di, w.x, -dr * w.y);  // (dr + i*di) * conj(w)
-    v[r] = make_float2(er - opi, ei + opr);
+  for (int r = 0; r < 16; ++r) {
+    const float2 z = v[br5(r)];
+    float2 p;
+    p.x = __shfl_sync(MST_FULL_MASK, v[br5(31 - r)].x, src);
+    p.y = __shfl_sync(MST_FULL_MASK, v[br5(31 - r)].y, src);
+    if (lane == 0) p = v[br5((32 - r) & 31)];  // lane 0 pairs with itself: bin 32*r <-> bin 32*(32-r); r = 0 -> Z[0]
+    pair_butterfly(z, p, twp[lane + 32 * r], o[r], o[31 - r]);
   }
-  if (lane == 0) v[0] = make_float2(0.5f * (y[0].x + nyq), 0.5f * (y[0].x - nyq));
-  __syncwarp();
+  {
+    const float2 z = v[br5(16)];  // lane 0: Z[512], its own partner
+    float2 dummy;
+    pair_butterfly(z, z, twp[512], *mid, dummy);
+  }
+}
+
+__device__ __forceinline__ void rfft2048_warp(float2 (&v)[32], float2 (&o)[32], float2* mid, float2* scratch,
+                                              const float2* tw1024, const float2* twp, int lane) {
+  fft1024_warp<-1>(v, scratch, tw1024, lane);
+  rfft_split(v, o, mid, twp, lane);
+}
+
+// Inverse real FFT from a mirror-layout spectrum y[0..31] (+ bin 512 in `mid` on lane 0).  Imaginary parts of the DC
+// and Nyquist bins are ignored (pocketfft c2r semantics).  Returns z[m] = x[2m] + i*x[2m+1], m = lane + 32*r, UNSCALED
+// by 1/1024, in v[br5(r)].
+__device__ __forceinline__ void irfft2048_warp(float2 (&y)[32], float2 mid, float2 (&v)[32], float2* scratch,
+                                               const float2* tw1024, const float2* twp, int lane) {
+  const int src = (32 - lane) & 31;
+  float2 t[16];  // merged values for bins 1024-k, to be handed to the mirrored lane
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    float2 a = y[r], b = y[31 - r];
+    if (r == 0 && lane == 0) { a.y = 0.0f; b.y = 0.0f; }  // DC / Nyquist
+    float2 w = twp[lane + 32 * r];
+    w.y = -w.y;
+    pair_butterfly(a, b, w, v[r], t[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    float2 got;
+    got.x = __shfl_sync(MST_FULL_MASK, t[r].x, src);
+    got.y = __shfl_sync(MST_FULL_MASK, t[r].y, src);
+    // lane 0 keeps its own: bin 32*(32-q) is element 32*(32-q) -> register 32-q, i.e. register 31-r takes q = r+1
+    if (lane == 0) got = (r < 15) ? t[r + 1] : make_float2(mid.x, -mid.y);  // register 16 = Z[512] = conj(Y[512])
+    v[31 - r] = got;
+  }
   fft1024_warp<+1>(v, scratch, tw1024, lane);
 }
 
-// Copy the 24 KB of constant tables into shared memory (all threads of the CTA participate).
-__device__ __forceinline__ void stage_tables(float2* s_tw1024, float2* s_tw2048, float* s_window,
-                                             const float2* g_tw1024, const float2* g_tw2048,
-                                             const float* g_window) {
-  const float4* a = reinterpret_cast<const float4*>(g_tw1024);
-  const float4* b = reinterpret_cast<const float4*>(g_tw2048);
-  const float4* c = reinterpret_cast<const float4*>(g_window);
-  float4* sa = reinterpret_cast<float4*>(s_tw1024);
-  float4* sb = reinterpret_cast<float4*>(s_tw2048);
-  float4* sc = reinterpret_cast<float4*>(s_window);
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-    sa[i] = __ldg(a + i);
-    sb[i] = __ldg(b + i);
-    sc[i] = __ldg(c + i);
-  }
+// Fast, accurate log1p for x >= 0: 2*atanh(x/(2+x)) series below 0.25, hardware log2 above.
+__device__ __forceinline__ float fast_log1p(float x) {
+  const float s = __fdividef(x, 2.0f + x);
+  const float s2 = s * s;
+  float poly = fmaf(s2, 1.0f / 9.0f, 1.0f / 7.0f);
+  poly = fmaf(s2, poly, 0.2f);
+  poly = fmaf(s2, poly, 1.0f / 3.0f);
+  poly = fmaf(s2, poly, 1.0f);
+  const float small = 2.0f * s * poly;
+  const float big = __log2f(1.0f + x) * 0.69314718055994530942f;
+  return x < 0.25f ? small : big;
 }
+
+// Cooperative copy of a 16-byte-aligned table into shared memory (n_vec4 float4 elements).
+__device__ __forceinline__ void stage_table(void* dst, const void* src, int n_vec4) {
+  const float4* a = reinterpret_cast<const float4*>(src);
+  float4* d = reinterpret_cast<float4*>(dst);
+  for (int i = threadIdx.x; i < n_vec4; i += blockDim.x) d[i] = __ldg(a + i);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// 16-byte asynchronous global -> shared copy (LDGSTS), bypassing registers and L1.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 }  // namespace mst

@@ -25,11 +25,14 @@ struct GlParams {
   const int32_t* tile_clip;
   int total_tiles;
   int hop;
+  int hop_shift;           // log2(hop) when hop is a power of two, else -1
+  int q_full;              // 2047 / hop: frames t in [q_full, T-1-q_full] see the periodic interior envelope
   int pad_mode;
   Tables tabs;
+  const float* wq;         // [2048] analysis window * interior 1/window-sum-square (period hop)
   const float* S;          // [total_frames][1025] magnitudes, frame-major
   float2* tprev;           // [total_frames][1025] previous rebuilt spectrum
-  const float* inv_wss;    // 1 / window-sum-square envelopes
+  const float* inv_wss;    // 1 / window-sum-square envelopes (edge frames)
   const int64_t* wss_off;  // per clip offset into inv_wss
   const float* acc_in;     // y_{j-1} (un-normalised overlap-add sums)
   float* acc_out;          // y_j accumulator (zero on entry)
@@ -52,32 +55,39 @@ __device__ __forceinline__ float uniform_hash(unsigned long long seed, unsigned 
   return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
-// Inverse transform of one frame's spectrum, window, and park the 2048 samples in this warp's slot.
-__device__ __forceinline__ void synthesize_frame(float2 (&y)[32], float nyq, float2* scratch, const float2* s_tw1024,
-                                                 const float2* s_tw2048, const float* s_window, int lane) {
+// Inverse transform of one frame's spectrum (mirror layout), synthesis window (1/1024 folded in), and park the 2048
+// samples in this warp's slot.
+__device__ __forceinline__ void synthesize_frame(float2 (&y)[32], float2 mid, float2* scratch, const float2* s_tw1024,
+                                                 const float2* s_twp, const float* s_wsyn, int lane) {
   float2 v[32];
-  irfft2048_warp(y, nyq, v, scratch, s_tw1024, s_tw2048, lane);
+  irfft2048_warp(y, mid, v, scratch, s_tw1024, s_twp, lane);
   __syncwarp();
-  const float2* w2 = reinterpret_cast<const float2*>(s_window);
-  const float scale = 1.0f / 1024.0f;
+  const float2* w2 = reinterpret_cast<const float2*>(s_wsyn);
 #pragma unroll
   for (int r = 0; r < 32; ++r) {
     const float2 w = w2[lane + 32 * r];
     const float2 z = v[br5(r)];
-    scratch[lane + 32 * r] = make_float2(z.x * scale * w.x, z.y * scale * w.y);  // samples 2m, 2m+1
+    scratch[lane + 32 * r] = make_float2(z.x * w.x, z.y * w.y);  // samples 2m, 2m+1
   }
 }
 
 // Sum the tile's frame slots in frame order and add the span to the global accumulator; zero the next accumulator.
-__device__ __forceinline__ void overlap_add_tile(const float* s_slots, const ClipDesc& cd, int t0, int hop,
+__device__ __forceinline__ void overlap_add_tile(const float* s_slots, const ClipDesc& cd, int t0, int hop, int hop_shift,
                                                  float* __restrict__ acc_out, float* __restrict__ acc_zero) {
   const int nvalid = min(kWarpsPerCta, cd.frames - t0);
   const int span = (nvalid - 1) * hop + kNfft;
   float* dst = acc_out + cd.acc_offset + (int64_t)t0 * hop;
   for (int p = threadIdx.x; p < span; p += blockDim.x) {
     int f_lo = p - (kNfft - 1);
-    f_lo = f_lo > 0 ? (f_lo + hop - 1) / hop : 0;
-    const int f_hi = min(nvalid - 1, p / hop);
+    int f_hi;
+    if (hop_shift >= 0) {
+      f_lo = f_lo > 0 ? (f_lo + hop - 1) >> hop_shift : 0;
+      f_hi = p >> hop_shift;
+    } else {
+      f_lo = f_lo > 0 ? (f_lo + hop - 1) / hop : 0;
+      f_hi = p / hop;
+    }
+    f_hi = min(nvalid - 1, f_hi);
     float sum = 0.0f;
     for (int f = f_lo; f <= f_hi; ++f) sum += s_slots[f * (2 * kScratchPerWarp) + p - f * hop];
     atomicAdd(dst + p, sum);
@@ -92,17 +102,32 @@ __device__ __forceinline__ void overlap_add_tile(const float* s_slots, const Cli
   }
 }
 
-template <bool INIT>
+constexpr size_t kGlSmemBytes = 8192 + sizeof(float2) * kTwpCount + 8192 + 8192 + sizeof(float2) * kScratchPerWarp * kWarpsPerCta;
+constexpr int kSpecStride = 1032;  // float2 elements per tprev row: 8256 B, 16-byte aligned rows for cp.async
+
+__device__ __forceinline__ float unit_scale(float ax, float ay) {
+  // 1 / (|a| + 1e-16) without a branch: |a| = m2 * rsqrt(m2) (guarded at 0), then one reciprocal
+  const float m2 = fmaf(ax, ax, ay * ay);
+  const float mag = m2 * rsqrtf(fmaxf(m2, 1e-37f));
+  return __fdividef(1.0f, mag + 1e-16f);
+}
+
+template <bool INIT, bool FIRST>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s_tw1024 = reinterpret_cast<float2*>(smem_raw);
-  float2* s_tw2048 = s_tw1024 + 1024;
-  float* s_window = reinterpret_cast<float*>(s_tw2048 + 1024);
-  float2* s_scratch_all = reinterpret_cast<float2*>(s_window + kNfft);
+  float2* s_twp = s_tw1024 + 1024;
+  float* s_wq = reinterpret_cast<float*>(s_twp + kTwpCount);
+  float* s_wsyn = s_wq + kNfft;
+  float2* s_scratch_all = reinterpret_cast<float2*>(s_wsyn + kNfft);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = mirror_base(lane);
   float2* scratch = s_scratch_all + warp * kScratchPerWarp;
 
-  stage_tables(s_tw1024, s_tw2048, s_window, P.tabs.tw1024, P.tabs.tw2048, P.tabs.window);
+  stage_table(s_tw1024, P.tabs.tw1024, 512);
+  stage_table(s_twp, P.tabs.twp, kTwpCount / 2);
+  stage_table(s_wq, P.wq, 512);
+  stage_table(s_wsyn, P.tabs.wsyn, 512);
   __syncthreads();
 
   for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -112,116 +137,128 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
     const int t = t0 + warp;
     const bool active = t < cd.frames;
     if (active) {
-      const int64_t row = (cd.frame_offset + t) * kBins;
+      const int64_t frame = cd.frame_offset + t;
+      const float* Srow = P.S + frame * kBins;
+      float2* trow = P.tprev + frame * kSpecStride;
+      // Start the HBM -> L2 fetch of this frame's target magnitudes now; they are consumed after the forward FFT.
+      for (int i = lane * 128; i < kBins * 4; i += 32 * 128) prefetch_l2(reinterpret_cast<const char*>(Srow) + i);
       float2 y[32];
-      float nyq;
+      float2 mid = make_float2(0.0f, 0.0f);
       if (INIT) {
         // y_0 = istft(S * exp(2*pi*i*u))
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const int k = lane + 32 * r;
+        for (int j = 0; j < 33; ++j) {
+          if (j == 32 && lane != 0) break;
+          const int k = j < 32 ? mirror_bin(lane, kb, j) : 512;
           float sn = 0.0f, cs = 1.0f;
           if (P.init_mode == 0) {
             float u;
             if (P.init_phase) {
               const int64_t idx = P.phase_layout == MST_LAYOUT_FRAME_MAJOR
-                                      ? row + k
+                                      ? frame * kBins + k
                                       : cd.frame_offset * kBins + (int64_t)k * cd.frames + t;
               u = __ldg(P.init_phase + idx);
             } else {
-              u = uniform_hash(P.seed, (unsigned long long)(row + k));
+              u = uniform_hash(P.seed, (unsigned long long)(frame * kBins + k));
             }
             sincospif(2.0f * u, &sn, &cs);
           }
-          const float s = __ldg(P.S + row + k);
-          y[r] = make_float2(s * cs, s * sn);
-        }
-        {
-          float sn = 0.0f, cs = 1.0f;
-          if (P.init_mode == 0) {
-            float u;
-            if (P.init_phase) {
-              const int64_t idx = P.phase_layout == MST_LAYOUT_FRAME_MAJOR
-                                      ? row + 1024
-                                      : cd.frame_offset * kBins + (int64_t)1024 * cd.frames + t;
-              u = __ldg(P.init_phase + idx);
-            } else {
-              u = uniform_hash(P.seed, (unsigned long long)(row + 1024));
-            }
-            sincospif(2.0f * u, &sn, &cs);
-          }
-          nyq = __ldg(P.S + row + 1024) * cs;  // irfft ignores the imaginary part of the Nyquist bin
+          const float s = __ldg(Srow + k);
+          const float2 val = make_float2(s * cs, s * sn);
+          if (j < 32) y[j] = val; else mid = val;
         }
       } else {
         // ---- re-analysis of y_{j-1}: reflect-padded frame, normalised by the window-sum-square envelope ----
         float2 v[32];
         const int64_t L = cd.length;                         // hop * (T - 1)
         const float* acc = P.acc_in + cd.acc_offset;         // acc[n + 1024] holds sample n before normalisation
-        const float* iw = P.inv_wss + __ldg(P.wss_off + c);
-        const int64_t base = (int64_t)t * P.hop - kHalf;  // first sample index of the frame (may be negative)
-        const bool interior = base >= 0 && base + kNfft <= L;
-        if (interior && ((base & 1) == 0)) {
-          const float2* a2 = reinterpret_cast<const float2*>(acc + base + kHalf);
-          const float2* w2 = reinterpret_cast<const float2*>(iw + base + kHalf);
+        const int64_t base = (int64_t)t * P.hop - kHalf;     // first sample index of the frame (may be negative)
+        const bool full = t >= P.q_full && t <= cd.frames - 1 - P.q_full && base >= 0 && base + kNfft <= L &&
+                          ((base & 1) == 0);
+        if (full) {
+          // interior frame: the envelope is periodic in hop and pre-multiplied into the analysis window
+          const float2* a2 = reinterpret_cast<const float2*>(acc + base + kHalf) + lane;
+          const float2* w2 = reinterpret_cast<const float2*>(s_wq) + lane;
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
-            const float2 a = a2[32 * r + lane];
-            const float2 w = __ldg(w2 + 32 * r + lane);
+            const float2 a = a2[32 * r];
+            const float2 w = w2[32 * r];
             v[r] = make_float2(a.x * w.x, a.y * w.y);
           }
         } else {
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            float s[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              int64_t n = base + 2 * (32 * r + lane) + h;
-              bool ok = true;
-              if (n < 0) {
-                if (P.pad_mode == MST_PAD_REFLECT) n = -n; else ok = false;
-              } else if (n >= L) {
-                if (P.pad_mode == MST_PAD_REFLECT) n = 2 * (L - 1) - n; else ok = false;
-              }
-              s[h] = ok ? acc[n + kHalf] * __ldg(iw + n + kHalf) : 0.0f;
+          // edge frame (rare): stage through this warp's scratch with a compact loop
+          const float* iw = P.inv_wss + __ldg(P.wss_off + c);
+          float* sf = reinterpret_cast<float*>(scratch);
+#pragma unroll 1
+          for (int jj = lane; jj < kNfft; jj += 32) {
+            int64_t n = base + jj;
+            bool ok = true;
+            if (n < 0) {
+              if (P.pad_mode == MST_PAD_REFLECT) n = -n; else ok = false;
+            } else if (n >= L) {
+              if (P.pad_mode == MST_PAD_REFLECT) n = 2 * (L - 1) - n; else ok = false;
             }
-            v[r] = make_float2(s[0], s[1]);
+            sf[jj] = ok ? acc[n + kHalf] * __ldg(iw + n + kHalf) * __ldg(P.tabs.window + jj) : 0.0f;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < 32; ++r) v[r] = scratch[32 * r + lane];
+          __syncwarp();
+        }
+        fft1024_front<-1>(v, scratch, s_tw1024, lane);
+        if (!FIRST) {
+          // previous iterate of this frame: HBM -> this warp's (now free) scratch tile, asynchronously, while the
+          // second FFT pass and the split butterflies run
+          const char* src = reinterpret_cast<const char*>(trow);
+          char* dst = reinterpret_cast<char*>(scratch);
+#pragma unroll
+          for (int i = 0; i < 17; ++i) {
+            const int o16 = (lane + 32 * i) * 16;
+            if (o16 < kSpecStride * 8) cp_async16(dst + o16, src + o16);
+          }
+          cp_async_commit();
+        }
+        fft32<-1>(v);
+        rfft_split(v, y, &mid, s_twp, lane);
+        if (!FIRST) {
+          cp_async_wait_all();
+          __syncwarp();
+        }
+        // ---- re-projection: momentum update, unit-modulus phase, target magnitude ----
+        const float* SA = Srow + lane;
+        const float* SB = Srow + kb;
+        float2* TA = trow + lane;
+        float2* TB = trow + kb;
+#pragma unroll
+        for (int g8 = 0; g8 < 32; g8 += 8) {
+          float sm[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sm[i] = __ldg((g8 < 16 ? SA : SB) + 32 * (g8 + i));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = g8 + i;
+            float2 tp = make_float2(0.0f, 0.0f);
+            if (!FIRST) tp = scratch[mirror_bin(lane, kb, j)];
+            (j < 16 ? TA : TB)[32 * j] = y[j];
+            const float ax = fmaf(-P.alpha, tp.x, y[j].x), ay = fmaf(-P.alpha, tp.y, y[j].y);
+            const float sc = sm[i] * unit_scale(ax, ay);
+            y[j] = make_float2(sc * ax, sc * ay);
           }
         }
-        const float2* win2 = reinterpret_cast<const float2*>(s_window);
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const float2 w = win2[32 * r + lane];
-          v[r].x *= w.x;
-          v[r].y *= w.y;
-        }
-        float xn;
-        rfft2048_warp(v, y, &xn, scratch, s_tw1024, s_tw2048, lane);
-        // ---- re-projection: momentum update, unit-modulus phase, target magnitude ----
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const int k = lane + 32 * r;
-          float2 tp = make_float2(0.0f, 0.0f);
-          if (!P.first_iter) tp = P.tprev[row + k];
-          P.tprev[row + k] = y[r];
-          const float ax = fmaf(-P.alpha, tp.x, y[r].x), ay = fmaf(-P.alpha, tp.y, y[r].y);
-          const float inv = 1.0f / (sqrtf(fmaf(ax, ax, ay * ay)) + 1e-16f);
-          const float s = __ldg(P.S + row + k);
-          y[r] = make_float2(s * ax * inv, s * ay * inv);
-        }
-        nyq = 0.0f;
         if (lane == 0) {
           float2 tp = make_float2(0.0f, 0.0f);
-          if (!P.first_iter) tp = P.tprev[row + 1024];
-          P.tprev[row + 1024] = make_float2(xn, 0.0f);
-          const float ax = fmaf(-P.alpha, tp.x, xn), ay = -P.alpha * tp.y;
-          const float inv = 1.0f / (sqrtf(fmaf(ax, ax, ay * ay)) + 1e-16f);
-          nyq = __ldg(P.S + row + 1024) * ax * inv;
+          if (!FIRST) tp = scratch[512];
+          trow[512] = mid;
+          const float ax = fmaf(-P.alpha, tp.x, mid.x), ay = fmaf(-P.alpha, tp.y, mid.y);
+          const float sc = __ldg(Srow + 512) * unit_scale(ax, ay);
+          mid = make_float2(sc * ax, sc * ay);
         }
+        __syncwarp();  // everyone is done reading the staged previous iterate before the inverse FFT reuses the tile
       }
-      synthesize_frame(y, nyq, scratch, s_tw1024, s_tw2048, s_window, lane);
+      synthesize_frame(y, mid, scratch, s_tw1024, s_twp, s_wsyn, lane);
     }
     __syncthreads();
-    overlap_add_tile(reinterpret_cast<const float*>(s_scratch_all), cd, t0, P.hop, P.acc_out, P.acc_zero);
+    overlap_add_tile(reinterpret_cast<const float*>(s_scratch_all), cd, t0, P.hop, P.hop_shift, P.acc_out, P.acc_zero);
     __syncthreads();
   }
 }
@@ -282,7 +319,7 @@ extern "C" {
 size_t mst_griffinlim_workspace_bytes(const mst_batch_t* b) {
   if (!b) return 0;
   const size_t spec = (size_t)b->total_frames * kBins;
-  return align_up(spec * sizeof(float2), 256) + align_up(spec * sizeof(float), 256) +
+  return align_up((size_t)b->total_frames * kSpecStride * sizeof(float2), 256) + align_up(spec * sizeof(float), 256) +
          3 * align_up((size_t)b->total_acc * sizeof(float), 256) + 256;
 }
 
@@ -305,7 +342,7 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
 
   const size_t spec = (size_t)b->total_frames * kBins;
   char* ws = reinterpret_cast<char*>(d_workspace);
-  float2* tprev = reinterpret_cast<float2*>(ws); ws += align_up(spec * sizeof(float2), 256);
+  float2* tprev = reinterpret_cast<float2*>(ws); ws += align_up((size_t)b->total_frames * kSpecStride * sizeof(float2), 256);
   float* S_t = reinterpret_cast<float*>(ws);     ws += align_up(spec * sizeof(float), 256);
   const size_t acc_bytes = align_up((size_t)b->total_acc * sizeof(float), 256);
   float* acc[3];
@@ -329,11 +366,12 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
   int dev = 0, sms = 0;
   MST_CUDA_OK(cudaGetDevice(&dev));
   MST_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t smem = kTableBytes + sizeof(float2) * kScratchPerWarp * kWarpsPerCta;
+  const size_t smem = kGlSmemBytes;
   static bool attr_set[64] = {false};
   if (!attr_set[dev]) {
-    MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[dev] = true;
   }
   const int grid = std::min(b->total_tiles, 2 * sms);
@@ -344,13 +382,17 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
   GlParams P{};
   P.clips = b->d_clips; P.tile_clip = b->d_tile_clip; P.total_tiles = b->total_tiles;
   P.hop = b->hop; P.pad_mode = b->pad_mode; P.tabs = tabs;
+  P.hop_shift = -1;
+  for (int sft = 0; sft < 12; ++sft) if ((1 << sft) == b->hop) P.hop_shift = sft;
+  P.q_full = (kNfft - 1) / b->hop;
+  P.wq = b->d_wq;
   P.S = S_use; P.tprev = tprev; P.inv_wss = b->d_inv_wss; P.wss_off = b->d_wss_offset;
   P.alpha = momentum / (1.0f + momentum);
   P.init_phase = d_init_phase; P.phase_layout = s_layout; P.init_mode = init_mode; P.seed = seed;
 
   // launch 0: y_0 from the initial phase, accumulated into acc[0]
   P.acc_in = nullptr; P.acc_out = acc[0]; P.acc_zero = nullptr; P.first_iter = 1;
-  gl_kernel<true><<<grid, kWarpsPerCta * 32, smem, s>>>(P);
+  gl_kernel<true, false><<<grid, kWarpsPerCta * 32, smem, s>>>(P);
   MST_CUDA_OK(cudaGetLastError());
   count_launch();
   int cur = 0;
@@ -359,7 +401,8 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
     P.acc_out = acc[(cur + 1) % 3];
     P.acc_zero = acc[(cur + 2) % 3];
     P.first_iter = (j == 1);
-    gl_kernel<false><<<grid, kWarpsPerCta * 32, smem, s>>>(P);
+    if (j == 1) gl_kernel<false, true><<<grid, kWarpsPerCta * 32, smem, s>>>(P);
+    else gl_kernel<false, false><<<grid, kWarpsPerCta * 32, smem, s>>>(P);
     MST_CUDA_OK(cudaGetLastError());
     count_launch();
     cur = (cur + 1) % 3;

@@ -29,11 +29,12 @@ void count_launch(int n = 1);
 // ---- constant tables (per device, built once on the host in double precision) ----------------
 struct Tables {
   const float2* tw1024;  // [32][32]: exp(-2*pi*i*k1*n2/1024)
-  const float2* tw2048;  // [1024]:   exp(-2*pi*i*k/2048)
+  const float2* twp;     // [520]:    -0.5i * exp(-2*pi*i*k/2048), k = 0..512 (real-FFT split twiddles, padded)
   const float* window;   // [2048]:   periodic Hann (scipy get_window('hann', 2048, fftbins=True))
+  const float* wsyn;     // [2048]:   window / 1024 (synthesis window with the inverse-FFT scale folded in)
 };
 int get_tables(Tables* out);  // for the current device
-constexpr int kTableBytes = 1024 * 8 + 1024 * 8 + 2048 * 4;  // 24 KB staged in shared memory
+constexpr int kTwpCount = 520;
 
 // ---- batch descriptor -------------------------------------------------------------------------
 struct ClipDesc {        // one per clip, device resident
@@ -57,6 +58,7 @@ struct mst_batch {
   mst::ClipDesc* h_clips = nullptr;  // host copy
   mst::ClipDesc* d_clips = nullptr;  // device copy
   int32_t* d_tile_clip = nullptr;    // [total_tiles] clip id of each frame tile
+  float* d_wq = nullptr;             // Griffin-Lim: analysis window * interior (hop-periodic) 1/window-sum-square
   float* d_inv_wss = nullptr;        // Griffin-Lim: 1 / window-sum-square per accumulator position (shared by equal-T clips)
   int64_t* d_wss_offset = nullptr;   // [n_clips] offset of the clip's envelope inside d_inv_wss
 };

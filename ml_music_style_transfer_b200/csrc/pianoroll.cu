@@ -97,47 +97,70 @@ __global__ void chunks_kernel(const int8_t* __restrict__ plane, int64_t n_rows, 
   }
 }
 
-// Audio-rate hold-replication.  Each thread produces one 16-byte vector of one key row; rows are written with
-// aligned 128-bit stores (scalar head / tail where a row does not start on a 16-byte boundary).
+// Audio-rate hold-replication: out[k][n] = plane[(n*fs)/sr][pitch_lo + k].  One warp owns a chunk of 32 x UP 16-byte
+// vectors of one key row (4096 int8 / 1024 float samples): fully coalesced 128-bit stores, one 64-bit division per
+// thread per chunk, column tracking by 32-bit remainder updates, and a broadcast fast path for the ~4 in 5 vectors that
+// sit inside a single roll column.  Rows need not start 16-byte aligned: scalar head / tail elements are written by the
+// warp that owns chunk 0.
+constexpr int kUpVec = 8;  // vectors per lane per chunk
+
 template <typename OUT>
-__global__ void upsample_kernel(const int8_t* __restrict__ plane, const int64_t* __restrict__ row_off,
-                                const int64_t* __restrict__ samp_off, int n_pieces, int fs, int sr, int pitch_lo,
-                                int n_keys, OUT* __restrict__ out) {
+__global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict__ plane, const int64_t* __restrict__ row_off,
+                                                       const int64_t* __restrict__ samp_off, int n_pieces, int fs, int sr,
+                                                       int pitch_lo, int n_keys, OUT* __restrict__ out) {
   constexpr int EPV = 16 / sizeof(OUT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
   for (int piece = blockIdx.z; piece < n_pieces; piece += gridDim.z) {
     const int64_t r0 = row_off[piece], T = row_off[piece + 1] - r0;
     const int64_t N = samp_off[piece + 1] - samp_off[piece];
-    const int8_t* src = plane + r0 * 128 + pitch_lo;
     for (int k = blockIdx.y; k < n_keys; k += gridDim.y) {
+      const int8_t* src = plane + r0 * 128 + pitch_lo + k;
       OUT* row = out + samp_off[piece] * n_keys + (int64_t)k * N;
       const int64_t mis = (int64_t)(((16 - (reinterpret_cast<uintptr_t>(row) & 15)) & 15) / sizeof(OUT));
       const int64_t head = mis < N ? mis : N;
       const int64_t nvec = (N - head) / EPV;
-      const int64_t tail0 = head + nvec * EPV;
-      // vector v covers samples [head + v*EPV, +EPV); pseudo-vectors nvec (head) and nvec+1 (tail) are scalar
-      for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec + 2; v += (int64_t)gridDim.x * blockDim.x) {
-        int64_t n0, cnt;
-        if (v < nvec) { n0 = head + v * EPV; cnt = EPV; }
-        else if (v == nvec) { n0 = 0; cnt = head; }
-        else { n0 = tail0; cnt = N - tail0; }
-        if (cnt <= 0) continue;
-        int64_t col = (n0 * fs) / sr;
-        int64_t rem = n0 * fs - col * sr;
-        OUT vals[EPV];
-        int8_t cur = col < T ? src[col * 128 + k] : (int8_t)0;
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) {
-          vals[e] = (OUT)cur;
-          rem += fs;
-          if (rem >= sr) {
-            do { rem -= sr; ++col; } while (rem >= sr);
-            cur = col < T ? src[col * 128 + k] : (int8_t)0;
+      const int64_t n_chunks = (nvec + 32 * kUpVec - 1) / (32 * kUpVec);
+      for (int64_t chunk = (int64_t)blockIdx.x * warps_per_cta + warp; chunk < (n_chunks > 0 ? n_chunks : 1);
+           chunk += (int64_t)gridDim.x * warps_per_cta) {
+        if (chunk == 0) {
+          // scalar head and tail of the row
+          const int64_t tail0 = head + nvec * EPV;
+          for (int64_t n = lane; n < head; n += 32) {
+            const int64_t col = (n * fs) / sr;
+            row[n] = (OUT)(col < T ? src[col * 128] : (int8_t)0);
+          }
+          for (int64_t n = tail0 + lane; n < N; n += 32) {
+            const int64_t col = (n * fs) / sr;
+            row[n] = (OUT)(col < T ? src[col * 128] : (int8_t)0);
           }
         }
-        if (cnt == EPV && v < nvec) {
+        const int64_t v0 = chunk * (32 * kUpVec);
+#pragma unroll
+        for (int u = 0; u < kUpVec; ++u) {
+          const int64_t v = v0 + u * 32 + lane;
+          if (v >= nvec) break;
+          const int64_t n0 = head + v * EPV;
+          const int64_t prod = n0 * fs;
+          int64_t col = prod / sr;
+          int rem = (int)(prod - col * sr);
+          int8_t cur = col < T ? src[col * 128] : (int8_t)0;
+          OUT vals[EPV];
+          if (rem + (EPV - 1) * fs < sr) {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) vals[e] = (OUT)cur;
+          } else {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+              vals[e] = (OUT)cur;
+              rem += fs;
+              if (rem >= sr) {
+                do { rem -= sr; ++col; } while (rem >= sr);
+                cur = col < T ? src[col * 128] : (int8_t)0;
+              }
+            }
+          }
           *reinterpret_cast<uint4*>(row + n0) = *reinterpret_cast<const uint4*>(vals);
-        } else {
-          for (int e = 0; e < cnt; ++e) row[n0 + e] = vals[e];
         }
       }
     }
@@ -220,7 +243,8 @@ int mst_pianoroll_upsample(const void* d_plane, const int64_t* d_row_offsets, co
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int64_t avg = total_samples / n_pieces + 1;
   const int epv = out_dtype == MST_DTYPE_I8 ? 16 : 4;
-  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (avg / epv + 255) / 256));
+  const int64_t chunks = (avg / epv + 32 * kUpVec - 1) / (32 * kUpVec);  // warp-chunks per key row (average piece)
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (chunks + 7) / 8));
   dim3 grid(gx, (unsigned)n_keys, (unsigned)std::min(n_pieces, 65535));
   const int8_t* src = reinterpret_cast<const int8_t*>(d_plane);
   switch (out_dtype) {

@@ -24,7 +24,7 @@ struct MelDev {            // device view of a mel plan (banded-compact filterba
 
 // Load one frame (centre-padded, reflect or zero) as z[m] = x[2m] + i*x[2m+1], m = 32*r + lane, times the window.
 __device__ __forceinline__ void load_frame(float2 (&v)[32], const float* __restrict__ clip, int64_t len, int64_t base,
-                                           int pad_mode, const float* s_window, int lane) {
+                                           int pad_mode, const float* s_window, float2* scratch, int lane) {
   const float2* w2 = reinterpret_cast<const float2*>(s_window);
   const bool interior = base >= 0 && base + kNfft <= len;
   if (interior && ((reinterpret_cast<uintptr_t>(clip + base) & 7) == 0)) {
@@ -32,22 +32,23 @@ __device__ __forceinline__ void load_frame(float2 (&v)[32], const float* __restr
 #pragma unroll
     for (int r = 0; r < 32; ++r) v[r] = __ldg(src + 32 * r + lane);
   } else {
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      float s[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        int64_t i = base + 2 * (32 * r + lane) + h;
-        bool ok = true;
-        if (i < 0) {
-          if (pad_mode == MST_PAD_REFLECT) i = -i; else ok = false;
-        } else if (i >= len) {
-          if (pad_mode == MST_PAD_REFLECT) i = 2 * (len - 1) - i; else ok = false;
-        }
-        s[h] = ok ? __ldg(clip + i) : 0.0f;
+    // edge or unaligned frame: stage through this warp's scratch with a compact (not unrolled) loop
+    float* sf = reinterpret_cast<float*>(scratch);
+#pragma unroll 1
+    for (int jj = lane; jj < kNfft; jj += 32) {
+      int64_t i = base + jj;
+      bool ok = true;
+      if (i < 0) {
+        if (pad_mode == MST_PAD_REFLECT) i = -i; else ok = false;
+      } else if (i >= len) {
+        if (pad_mode == MST_PAD_REFLECT) i = 2 * (len - 1) - i; else ok = false;
       }
-      v[r] = make_float2(s[0], s[1]);
+      sf[jj] = ok ? __ldg(clip + i) : 0.0f;
     }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) v[r] = scratch[32 * r + lane];
+    __syncwarp();
   }
 #pragma unroll
   for (int r = 0; r < 32; ++r) {
@@ -61,9 +62,11 @@ template <int MODE>
 __device__ __forceinline__ float epilogue_value(float2 x) {
   const float p = fmaf(x.x, x.x, x.y * x.y);
   if (MODE == MST_OUT_MAGNITUDE) return sqrtf(p);
-  if (MODE == MST_OUT_LOG1P_POWER) return log1pf(p);
+  if (MODE == MST_OUT_LOG1P_POWER) return fast_log1p(p);
   return p;
 }
+
+constexpr size_t kStftSmemBytes = 8192 + sizeof(float2) * kTwpCount + 8192 + sizeof(float2) * kScratchPerWarp * kWarpsPerCta;
 
 template <int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
@@ -71,14 +74,17 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
             int total_tiles, int hop, int pad_mode, Tables tabs, int layout, void* __restrict__ out_v, MelDev mel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s_tw1024 = reinterpret_cast<float2*>(smem_raw);
-  float2* s_tw2048 = s_tw1024 + 1024;
-  float* s_window = reinterpret_cast<float*>(s_tw2048 + 1024);
+  float2* s_twp = s_tw1024 + 1024;
+  float* s_window = reinterpret_cast<float*>(s_twp + kTwpCount);
   float2* s_scratch_all = reinterpret_cast<float2*>(s_window + kNfft);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = mirror_base(lane);
   float2* scratch = s_scratch_all + warp * kScratchPerWarp;
   float* s_tile = reinterpret_cast<float*>(s_scratch_all);  // bin-major staging tile aliases the scratch region
 
-  stage_tables(s_tw1024, s_tw2048, s_window, tabs.tw1024, tabs.tw2048, tabs.window);
+  stage_table(s_tw1024, tabs.tw1024, 512);
+  stage_table(s_twp, tabs.twp, kTwpCount / 2);
+  stage_table(s_window, tabs.window, 512);
   __syncthreads();
 
   const int n_out = (MODE == kModeMel) ? mel.n_mels : kBins;  // values per frame in the output
@@ -89,12 +95,25 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
     const int t0 = (tile - cd.tile_offset) * kWarpsPerCta;
     const int t = t0 + warp;
     const bool active = t < cd.frames;
-    float2 x[32];
-    float nyq = 0.0f;
+    {  // pull the audio of this CTA's next tile towards L2 while this one computes
+      const int nt = tile + gridDim.x;
+      if (nt < total_tiles && warp == 0) {
+        const int c2 = __ldg(tile_clip + nt);
+        const ClipDesc cn = clips[c2];
+        const int64_t b0 = (int64_t)(nt - cn.tile_offset) * kWarpsPerCta * hop - kHalf;
+        const int64_t span = (int64_t)(kWarpsPerCta - 1) * hop + kNfft;
+        for (int64_t i = (int64_t)lane * 32; i < span; i += 32 * 32) {
+          const int64_t idx = b0 + i;
+          if (idx >= 0 && idx < cn.length) prefetch_l2(audio + cn.sample_offset + idx);
+        }
+      }
+    }
+    float2 o[32];
+    float2 mid = make_float2(0.0f, 0.0f);
     if (active) {
       float2 v[32];
-      load_frame(v, audio + cd.sample_offset, cd.length, (int64_t)t * hop - kHalf, pad_mode, s_window, lane);
-      rfft2048_warp(v, x, &nyq, scratch, s_tw1024, s_tw2048, lane);
+      load_frame(v, audio + cd.sample_offset, cd.length, (int64_t)t * hop - kHalf, pad_mode, s_window, scratch, lane);
+      rfft2048_warp(v, o, &mid, scratch, s_tw1024, s_twp, lane);
     }
     const int64_t g = cd.frame_offset + t;  // global frame id
 
@@ -102,8 +121,8 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
       if (active) {
         float2* out = reinterpret_cast<float2*>(out_v) + g * kBins;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) out[lane + 32 * r] = x[r];
-        if (lane == 0) out[1024] = make_float2(nyq, 0.0f);
+        for (int j = 0; j < 32; ++j) out[mirror_bin(lane, kb, j)] = o[j];
+        if (lane == 0) out[512] = mid;
       }
       continue;
     }
@@ -113,10 +132,11 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
     if (MODE == kModeMel) {
       // power spectrum of this frame -> this warp's scratch (linear [k]), then banded mel rows per lane
       float* pw = reinterpret_cast<float*>(scratch);
+      __syncwarp();
       if (active) {
 #pragma unroll
-        for (int r = 0; r < 32; ++r) pw[lane + 32 * r] = fmaf(x[r].x, x[r].x, x[r].y * x[r].y);
-        if (lane == 0) pw[1024] = nyq * nyq;
+        for (int j = 0; j < 32; ++j) pw[mirror_bin(lane, kb, j)] = fmaf(o[j].x, o[j].x, o[j].y * o[j].y);
+        if (lane == 0) pw[512] = fmaf(mid.x, mid.x, mid.y * mid.y);
       }
       __syncwarp();
       float melv[8];  // n_mels <= 256
@@ -129,7 +149,7 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
           const float* wr = mel.w + __ldg(mel.woff + m);
           float acc = 0.0f;
           for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(wr + j), pw[k0 + j], acc);
-          melv[i] = mel.apply_log1p ? log1pf(acc) : acc;
+          melv[i] = mel.apply_log1p ? fast_log1p(acc) : acc;
         }
       }
       __syncwarp();
@@ -156,15 +176,15 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
         if (active) {
           float* row = out + g * kBins;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) row[lane + 32 * r] = epilogue_value<MODE>(x[r]);
-          if (lane == 0) row[1024] = epilogue_value<MODE>(make_float2(nyq, 0.0f));
+          for (int j = 0; j < 32; ++j) row[mirror_bin(lane, kb, j)] = epilogue_value<MODE>(o[j]);
+          if (lane == 0) row[512] = epilogue_value<MODE>(mid);
         }
       } else {
         __syncthreads();
         if (active) {
 #pragma unroll
-          for (int r = 0; r < 32; ++r) s_tile[warp * kTileStride + lane + 32 * r] = epilogue_value<MODE>(x[r]);
-          if (lane == 0) s_tile[warp * kTileStride + 1024] = epilogue_value<MODE>(make_float2(nyq, 0.0f));
+          for (int j = 0; j < 32; ++j) s_tile[warp * kTileStride + mirror_bin(lane, kb, j)] = epilogue_value<MODE>(o[j]);
+          if (lane == 0) s_tile[warp * kTileStride + 512] = epilogue_value<MODE>(mid);
         }
       }
     }
@@ -188,7 +208,7 @@ static int launch_stft(const float* d_audio, const mst_batch* b, int layout, voi
   Tables tabs;
   int rc = get_tables(&tabs);
   if (rc) return rc;
-  const size_t smem = kTableBytes + sizeof(float2) * kScratchPerWarp * kWarpsPerCta;
+  const size_t smem = kStftSmemBytes;
   static bool attr_set[64] = {false};
   int dev = 0;
   MST_CUDA_OK(cudaGetDevice(&dev));
