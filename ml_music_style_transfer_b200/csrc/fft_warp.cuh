@@ -17,51 +17,74 @@ __host__ __device__ __forceinline__ constexpr int br5(int k) {
   return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
 }
 
-// cos / sin of 2*pi*q/32 for q in [0,16)
-__device__ __forceinline__ constexpr float cos32(int q) {
-  return q == 0   ? 1.0f
-         : q == 1 ? 0.98078528040323044913f
-         : q == 2 ? 0.92387953251128675613f
-         : q == 3 ? 0.83146961230254523708f
-         : q == 4 ? 0.70710678118654752440f
-         : q == 5 ? 0.55557023301960222474f
-         : q == 6 ? 0.38268343236508977173f
-         : q == 7 ? 0.19509032201612826785f
-         : q == 8 ? 0.0f
-                  : -cos32(16 - q);
-}
-__device__ __forceinline__ constexpr float sin32(int q) { return q <= 8 ? cos32(8 - q) : cos32(q - 8); }
+// cos / sin of 2*pi*q/32 for q in [0,16]: plain constant tables so that, after full unrolling, every twiddle folds
+// into an immediate operand (a recursive constexpr helper was NOT folded by nvcc and ended up as real calls).
+#define MST_C1 0.98078528040323044913f
+#define MST_C2 0.92387953251128675613f
+#define MST_C3 0.83146961230254523708f
+#define MST_C4 0.70710678118654752440f
+#define MST_C5 0.55557023301960222474f
+#define MST_C6 0.38268343236508977173f
+#define MST_C7 0.19509032201612826785f
+template <int Q>
+struct Tw32 {
+  static_assert(Q >= 0 && Q <= 16, "twiddle index");
+  __host__ __device__ static constexpr float cosv() {
+    constexpr float t[17] = {1.0f, MST_C1, MST_C2, MST_C3, MST_C4, MST_C5, MST_C6, MST_C7, 0.0f,
+                             -MST_C7, -MST_C6, -MST_C5, -MST_C4, -MST_C3, -MST_C2, -MST_C1, -1.0f};
+    return t[Q];
+  }
+  __host__ __device__ static constexpr float sinv() {
+    constexpr float t[17] = {0.0f, MST_C7, MST_C6, MST_C5, MST_C4, MST_C3, MST_C2, MST_C1, 1.0f,
+                             MST_C1, MST_C2, MST_C3, MST_C4, MST_C5, MST_C6, MST_C7, 0.0f};
+    return t[Q];
+  }
+};
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
+// One radix-2 DIF butterfly with the compile-time twiddle W_32^Q (forward) / conj (inverse).
+template <int SIGN, int Q>
+__device__ __forceinline__ void bfly(float2& a, float2& b) {
+  const float dx = a.x - b.x, dy = a.y - b.y;
+  a = make_float2(a.x + b.x, a.y + b.y);
+  if (Q == 0) {
+    b = make_float2(dx, dy);
+  } else if (Q == 8) {  // multiply by SIGN * i
+    b = SIGN < 0 ? make_float2(dy, -dx) : make_float2(-dy, dx);
+  } else if (Q == 4) {  // (1 + SIGN*i) / sqrt(2)
+    constexpr float c = MST_C4;
+    b = SIGN < 0 ? make_float2((dx + dy) * c, (dy - dx) * c) : make_float2((dx - dy) * c, (dy + dx) * c);
+  } else if (Q == 12) {  // (-1 + SIGN*i) / sqrt(2)
+    constexpr float c = MST_C4;
+    b = SIGN < 0 ? make_float2((dy - dx) * c, -(dx + dy) * c) : make_float2(-(dx + dy) * c, (dx - dy) * c);
+  } else {
+    constexpr float wr = Tw32<Q>::cosv();
+    constexpr float wi = SIGN * Tw32<Q>::sinv();
+    b = make_float2(fmaf(dx, wr, -dy * wi), fmaf(dx, wi, dy * wr));
+  }
+}
+
+template <int SIGN, int HALF, int G, int J>
+struct StageLoop {
+  __device__ __forceinline__ static void run(float2 (&v)[32]) {
+    bfly<SIGN, J*(16 / HALF)>(v[G + J], v[G + J + HALF]);
+    if constexpr (J + 1 < HALF) StageLoop<SIGN, HALF, G, J + 1>::run(v);
+    else if constexpr (G + 2 * HALF < 32) StageLoop<SIGN, HALF, G + 2 * HALF, 0>::run(v);
+  }
+};
+
 // In-register radix-2 DIF FFT-32.  SIGN = -1 forward, +1 inverse (unnormalised).
 // Output X[k] is left in v[br5(k)].
 template <int SIGN>
 __device__ __forceinline__ void fft32(float2 (&v)[32]) {
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    const int half = 16 >> s;
-#pragma unroll
-    for (int g = 0; g < 32; g += 2 * half) {
-#pragma unroll
-      for (int j = 0; j < half; ++j) {
-        const int q = j * (16 / half);
-        const float2 a = v[g + j], b = v[g + j + half];
-        v[g + j] = make_float2(a.x + b.x, a.y + b.y);
-        const float dx = a.x - b.x, dy = a.y - b.y;
-        if (q == 0) {
-          v[g + j + half] = make_float2(dx, dy);
-        } else if (q == 8) {  // multiply by SIGN * i
-          v[g + j + half] = SIGN < 0 ? make_float2(dy, -dx) : make_float2(-dy, dx);
-        } else {
-          const float wr = cos32(q), wi = SIGN * sin32(q);
-          v[g + j + half] = make_float2(fmaf(dx, wr, -dy * wi), fmaf(dx, wi, dy * wr));
-        }
-      }
-    }
-  }
+  StageLoop<SIGN, 16, 0, 0>::run(v);
+  StageLoop<SIGN, 8, 0, 0>::run(v);
+  StageLoop<SIGN, 4, 0, 0>::run(v);
+  StageLoop<SIGN, 2, 0, 0>::run(v);
+  StageLoop<SIGN, 1, 0, 0>::run(v);
 }
 
 // 1024-point complex FFT across one warp.  `scratch` is this warp's 32x33 float2 tile,
