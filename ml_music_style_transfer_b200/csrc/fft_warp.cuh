@@ -1,7 +1,7 @@
 // Warp-level 1024-point complex FFT (and the 2048-point real transforms built on it).
 //
 // One warp owns one frame.  N = 1024 = 32 x 32 (Cooley-Tukey): lane l, register r hold element
-// 32*r + l.  Pass 1 is a radix-2 DIF FFT-32 entirely in registers (compile-time twiddles), then the
+// 32*r + l.  Pass 1 is a radix-2 DIT FFT-32 entirely in registers (compile-time twiddles), then the
 // W_1024^(k1*n2) twiddles, a 32x32 transpose through a padded per-warp shared-memory tile, and pass 2
 // (another in-register FFT-32).  Output element k = l + 32*r sits in register slot BR5(r) of lane l,
 // i.e. the output layout equals the input layout, so forward and inverse chain without reshuffles.
@@ -45,46 +45,64 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-// One radix-2 DIF butterfly with the compile-time twiddle W_32^Q (forward) / conj (inverse).
+// One radix-2 decimation-in-time butterfly with the compile-time twiddle w = W_32^Q (forward) / conj (inverse):
+//   t = w*b;  a' = a + t;  b' = a - t = 2a - a'.
+// Written so that the general case is 6 FMAs (a' by two nested FMAs per component, b' = fma(2, a, -a')) and the
+// sqrt(1/2) twiddles are 2 adds + 4 FMAs; multiplications by 1 and -+i are 4 adds.
 template <int SIGN, int Q>
 __device__ __forceinline__ void bfly(float2& a, float2& b) {
-  const float dx = a.x - b.x, dy = a.y - b.y;
-  a = make_float2(a.x + b.x, a.y + b.y);
   if (Q == 0) {
-    b = make_float2(dx, dy);
-  } else if (Q == 8) {  // multiply by SIGN * i
-    b = SIGN < 0 ? make_float2(dy, -dx) : make_float2(-dy, dx);
-  } else if (Q == 4) {  // (1 + SIGN*i) / sqrt(2)
+    const float2 t = b;
+    b = make_float2(a.x - t.x, a.y - t.y);
+    a = make_float2(a.x + t.x, a.y + t.y);
+  } else if (Q == 8) {  // w = SIGN * i:  t = SIGN * (-b.y, b.x)
+    const float tx = SIGN < 0 ? b.y : -b.y, ty = SIGN < 0 ? -b.x : b.x;
+    b = make_float2(a.x - tx, a.y - ty);
+    a = make_float2(a.x + tx, a.y + ty);
+  } else if (Q == 4 || Q == 12) {
+    // Q=4:  w = c*(1 + SIGN*i)  -> t = c*(b.x - SIGN*b.y, b.y + SIGN*b.x)
+    // Q=12: w = c*(-1 + SIGN*i) -> t = c*(-b.x - SIGN*b.y, -b.y + SIGN*b.x)
     constexpr float c = MST_C4;
-    b = SIGN < 0 ? make_float2((dx + dy) * c, (dy - dx) * c) : make_float2((dx - dy) * c, (dy + dx) * c);
-  } else if (Q == 12) {  // (-1 + SIGN*i) / sqrt(2)
-    constexpr float c = MST_C4;
-    b = SIGN < 0 ? make_float2((dy - dx) * c, -(dx + dy) * c) : make_float2(-(dx + dy) * c, (dx - dy) * c);
+    float ux, uy;
+    if (Q == 4) {
+      ux = SIGN < 0 ? b.x + b.y : b.x - b.y;
+      uy = SIGN < 0 ? b.y - b.x : b.y + b.x;
+    } else {
+      ux = SIGN < 0 ? b.y - b.x : -(b.x + b.y);
+      uy = SIGN < 0 ? -(b.x + b.y) : b.x - b.y;
+    }
+    const float ax = fmaf(c, ux, a.x), ay = fmaf(c, uy, a.y);
+    b = make_float2(fmaf(2.0f, a.x, -ax), fmaf(2.0f, a.y, -ay));
+    a = make_float2(ax, ay);
   } else {
     constexpr float wr = Tw32<Q>::cosv();
     constexpr float wi = SIGN * Tw32<Q>::sinv();
-    b = make_float2(fmaf(dx, wr, -dy * wi), fmaf(dx, wi, dy * wr));
+    const float ax = fmaf(wr, b.x, fmaf(-wi, b.y, a.x));
+    const float ay = fmaf(wr, b.y, fmaf(wi, b.x, a.y));
+    b = make_float2(fmaf(2.0f, a.x, -ax), fmaf(2.0f, a.y, -ay));
+    a = make_float2(ax, ay);
   }
 }
 
+// Stage with butterfly span HALF over the conceptual array u[i] = v[br5(i)] (bit-reversed input == natural v[]).
 template <int SIGN, int HALF, int G, int J>
 struct StageLoop {
   __device__ __forceinline__ static void run(float2 (&v)[32]) {
-    bfly<SIGN, J*(16 / HALF)>(v[G + J], v[G + J + HALF]);
+    bfly<SIGN, J*(16 / HALF)>(v[br5(G + J)], v[br5(G + J + HALF)]);
     if constexpr (J + 1 < HALF) StageLoop<SIGN, HALF, G, J + 1>::run(v);
     else if constexpr (G + 2 * HALF < 32) StageLoop<SIGN, HALF, G + 2 * HALF, 0>::run(v);
   }
 };
 
-// In-register radix-2 DIF FFT-32.  SIGN = -1 forward, +1 inverse (unnormalised).
-// Output X[k] is left in v[br5(k)].
+// In-register radix-2 DIT FFT-32.  SIGN = -1 forward, +1 inverse (unnormalised).
+// Input x[n] in v[n]; output X[k] is left in v[br5(k)].
 template <int SIGN>
 __device__ __forceinline__ void fft32(float2 (&v)[32]) {
-  StageLoop<SIGN, 16, 0, 0>::run(v);
-  StageLoop<SIGN, 8, 0, 0>::run(v);
-  StageLoop<SIGN, 4, 0, 0>::run(v);
-  StageLoop<SIGN, 2, 0, 0>::run(v);
   StageLoop<SIGN, 1, 0, 0>::run(v);
+  StageLoop<SIGN, 2, 0, 0>::run(v);
+  StageLoop<SIGN, 4, 0, 0>::run(v);
+  StageLoop<SIGN, 8, 0, 0>::run(v);
+  StageLoop<SIGN, 16, 0, 0>::run(v);
 }
 
 // 1024-point complex FFT across one warp.  `scratch` is this warp's 32x33 float2 tile,

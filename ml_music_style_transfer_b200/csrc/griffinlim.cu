@@ -72,25 +72,35 @@ __device__ __forceinline__ void synthesize_frame(float2 (&y)[32], float2 mid, fl
 }
 
 // Sum the tile's frame slots in frame order and add the span to the global accumulator; zero the next accumulator.
+// When hop divides n_fft the span is walked hop-block by hop-block: block b of the span receives frames
+// f = b-R+1 .. b (R = n_fft / hop), bounds that are uniform across the CTA, so the inner loop has no divergence and no
+// divisions.  Other hops use a generic per-sample form.
 __device__ __forceinline__ void overlap_add_tile(const float* s_slots, const ClipDesc& cd, int t0, int hop, int hop_shift,
                                                  float* __restrict__ acc_out, float* __restrict__ acc_zero) {
   const int nvalid = min(kWarpsPerCta, cd.frames - t0);
-  const int span = (nvalid - 1) * hop + kNfft;
   float* dst = acc_out + cd.acc_offset + (int64_t)t0 * hop;
-  for (int p = threadIdx.x; p < span; p += blockDim.x) {
-    int f_lo = p - (kNfft - 1);
-    int f_hi;
-    if (hop_shift >= 0) {
-      f_lo = f_lo > 0 ? (f_lo + hop - 1) >> hop_shift : 0;
-      f_hi = p >> hop_shift;
-    } else {
-      f_lo = f_lo > 0 ? (f_lo + hop - 1) / hop : 0;
-      f_hi = p / hop;
+  constexpr int kSlot = 2 * kScratchPerWarp;  // floats between consecutive frame slots
+  if (hop_shift >= 0) {
+    const int R = kNfft >> hop_shift;
+    const int n_blocks = nvalid - 1 + R;
+    for (int b = 0; b < n_blocks; ++b) {
+      const int f_lo = max(0, b - R + 1), f_hi = min(b, nvalid - 1);
+      for (int j = threadIdx.x; j < hop; j += blockDim.x) {
+        float sum = 0.0f;
+        for (int f = f_lo; f <= f_hi; ++f) sum += s_slots[f * kSlot + ((b - f) << hop_shift) + j];
+        atomicAdd(dst + (b << hop_shift) + j, sum);
+      }
     }
-    f_hi = min(nvalid - 1, f_hi);
-    float sum = 0.0f;
-    for (int f = f_lo; f <= f_hi; ++f) sum += s_slots[f * (2 * kScratchPerWarp) + p - f * hop];
-    atomicAdd(dst + p, sum);
+  } else {
+    const int span = (nvalid - 1) * hop + kNfft;
+    for (int p = threadIdx.x; p < span; p += blockDim.x) {
+      int f_lo = p - (kNfft - 1);
+      f_lo = f_lo > 0 ? (f_lo + hop - 1) / hop : 0;
+      const int f_hi = min(nvalid - 1, p / hop);
+      float sum = 0.0f;
+      for (int f = f_lo; f <= f_hi; ++f) sum += s_slots[f * kSlot + p - f * hop];
+      atomicAdd(dst + p, sum);
+    }
   }
   if (acc_zero) {
     const int64_t acc_len = kNfft + (int64_t)hop * (cd.frames - 1);
@@ -136,6 +146,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
     const int t0 = (tile - cd.tile_offset) * kWarpsPerCta;
     const int t = t0 + warp;
     const bool active = t < cd.frames;
+    if (!INIT && warp == 0) {  // pull the accumulator span of this CTA's next tile towards L2
+      const int nt = tile + gridDim.x;
+      if (nt < P.total_tiles) {
+        const ClipDesc cn = P.clips[__ldg(P.tile_clip + nt)];
+        const float* a = P.acc_in + cn.acc_offset + (int64_t)(nt - cn.tile_offset) * kWarpsPerCta * P.hop;
+        const int span = (kWarpsPerCta - 1) * P.hop + kNfft;
+        for (int i = lane * 32; i < span; i += 32 * 32) prefetch_l2(a + i);
+      }
+    }
     if (active) {
       const int64_t frame = cd.frame_offset + t;
       const float* Srow = P.S + frame * kBins;

@@ -97,12 +97,31 @@ __global__ void chunks_kernel(const int8_t* __restrict__ plane, int64_t n_rows, 
   }
 }
 
-// Audio-rate hold-replication: out[k][n] = plane[(n*fs)/sr][pitch_lo + k].  One warp owns a chunk of 32 x UP 16-byte
-// vectors of one key row (4096 int8 / 1024 float samples): fully coalesced 128-bit stores, one 64-bit division per
-// thread per chunk, column tracking by 32-bit remainder updates, and a broadcast fast path for the ~4 in 5 vectors that
-// sit inside a single roll column.  Rows need not start 16-byte aligned: scalar head / tail elements are written by the
-// warp that owns chunk 0.
+// Audio-rate hold-replication: out[k][n] = plane[(n*fs)/sr][pitch_lo + k].  One warp owns a chunk of 32 x kUpVec 16-byte
+// vectors of one key row (4096 int8 / 1024 float samples): fully coalesced 128-bit stores, ONE 64-bit division per
+// thread per chunk (the column / remainder pair is then advanced incrementally), and a branch-free split of each vector
+// at its (single) column crossing: the number of samples left in the current column comes from a multiply-high by a
+// precomputed reciprocal of fs.  Rows need not start 16-byte aligned: scalar head / tail elements are written by the
+// warp that owns chunk 0.  If one vector could span more than two columns (fs * EPV > sr) a generic loop is used.
 constexpr int kUpVec = 8;  // vectors per lane per chunk
+
+template <typename OUT>
+__device__ __forceinline__ void make_vector(OUT (&vals)[16 / sizeof(OUT)], int8_t cur, int8_t nxt, int e_cross) {
+  constexpr int EPV = 16 / sizeof(OUT);
+  if (sizeof(OUT) == 1) {
+    const unsigned c4 = (unsigned)(uint8_t)cur * 0x01010101u, n4 = (unsigned)(uint8_t)nxt * 0x01010101u;
+    unsigned* w = reinterpret_cast<unsigned*>(vals);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = e_cross - 4 * i;  // bytes of this word that still belong to the current column
+      const unsigned m = k >= 4 ? 0u : (k <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * k)));
+      w[i] = (c4 & ~m) | (n4 & m);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) vals[e] = (OUT)(e < e_cross ? cur : nxt);
+  }
+}
 
 template <typename OUT>
 __global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict__ plane, const int64_t* __restrict__ row_off,
@@ -111,6 +130,9 @@ __global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict_
   constexpr int EPV = 16 / sizeof(OUT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_cta = blockDim.x >> 5;
+  const bool simple = (int64_t)fs * EPV <= sr;                // at most one column crossing per vector
+  const unsigned fs_magic = (unsigned)(0x100000000ull / (unsigned)fs) + 1u;  // exact ceil-div by fs for numerators < 2^32/fs
+  const int step_col = (32 * EPV * fs) / sr, step_rem = (32 * EPV * fs) % sr;  // advance of 32 vectors
   for (int piece = blockIdx.z; piece < n_pieces; piece += gridDim.z) {
     const int64_t r0 = row_off[piece], T = row_off[piece + 1] - r0;
     const int64_t N = samp_off[piece + 1] - samp_off[piece];
@@ -135,32 +157,40 @@ __global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict_
             row[n] = (OUT)(col < T ? src[col * 128] : (int8_t)0);
           }
         }
-        const int64_t v0 = chunk * (32 * kUpVec);
+        int64_t v = chunk * (32 * kUpVec) + lane;
+        const int64_t prod = (head + v * EPV) * fs;
+        int64_t col = prod / sr;
+        int rem = (int)(prod - col * sr);
 #pragma unroll
         for (int u = 0; u < kUpVec; ++u) {
-          const int64_t v = v0 + u * 32 + lane;
           if (v >= nvec) break;
-          const int64_t n0 = head + v * EPV;
-          const int64_t prod = n0 * fs;
-          int64_t col = prod / sr;
-          int rem = (int)(prod - col * sr);
-          int8_t cur = col < T ? src[col * 128] : (int8_t)0;
+          OUT* dst = row + head + v * EPV;
           OUT vals[EPV];
-          if (rem + (EPV - 1) * fs < sr) {
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) vals[e] = (OUT)cur;
+          const int8_t cur = col < T ? src[col * 128] : (int8_t)0;
+          if (simple) {
+            const int8_t nxt = col + 1 < T ? src[(col + 1) * 128] : (int8_t)0;
+            // samples e with rem + e*fs < sr stay in `col`: e_cross = ceil((sr - rem) / fs)
+            const int e_cross = (int)__umulhi((unsigned)(sr - rem + fs - 1), fs_magic);
+            make_vector<OUT>(vals, cur, nxt, e_cross);
           } else {
-#pragma unroll
+            int64_t c2 = col;
+            int r2 = rem;
+            int8_t cv = cur;
+#pragma unroll 1
             for (int e = 0; e < EPV; ++e) {
-              vals[e] = (OUT)cur;
-              rem += fs;
-              if (rem >= sr) {
-                do { rem -= sr; ++col; } while (rem >= sr);
-                cur = col < T ? src[col * 128] : (int8_t)0;
+              vals[e] = (OUT)cv;
+              r2 += fs;
+              if (r2 >= sr) {
+                do { r2 -= sr; ++c2; } while (r2 >= sr);
+                cv = c2 < T ? src[c2 * 128] : (int8_t)0;
               }
             }
           }
-          *reinterpret_cast<uint4*>(row + n0) = *reinterpret_cast<const uint4*>(vals);
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals);
+          v += 32;
+          col += step_col;
+          rem += step_rem;
+          if (rem >= sr) { rem -= sr; ++col; }
         }
       }
     }
