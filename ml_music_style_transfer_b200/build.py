@@ -12,8 +12,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-CUDA_SOURCES = ["core.cu", "stft.cu", "griffinlim.cu", "pianoroll.cu"]
-HEADERS = ["mst_common.cuh", "fft_warp.cuh", os.path.join("..", "..", "include", "mst_b200.h")]
+CUDA_SOURCES = ["core.cu", "stft.cu", "mel_gemm.cu", "griffinlim.cu", "pianoroll.cu"]
+HEADERS = ["mst_common.cuh", "fft_warp.cuh", "mel_plan.cuh", os.path.join("..", "..", "include", "mst_b200.h")]
 LIB_CUDA = os.path.join(HERE, "libmst_b200.so")
 LIB_OPS = os.path.join(HERE, "libmst_torch_ops.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -101,6 +101,9 @@ static int batch_finish(mst_batch* b) {
   b->total_samples = samples;
   b->total_acc = acc_off;
   b->total_tiles = (int)tile_off;
+  b->uniform_frames = b->h_clips[0].frames;
+  for (int c = 1; c < b->n_clips; ++c)
+    if (b->h_clips[c].frames != b->uniform_frames) { b->uniform_frames = 0; break; }
   MST_CUDA_OK(cudaGetDevice(&b->device));
   MST_CUDA_OK(cudaMalloc(&b->d_clips, sizeof(ClipDesc) * (size_t)b->n_clips));
   MST_CUDA_OK(cudaMemcpy(b->d_clips, b->h_clips, sizeof(ClipDesc) * (size_t)b->n_clips, cudaMemcpyHostToDevice));

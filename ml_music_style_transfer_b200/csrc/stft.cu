@@ -6,20 +6,18 @@
 #include <algorithm>
 #include <vector>
 #include "fft_warp.cuh"
+#include "mel_plan.cuh"
 #include "mst_common.cuh"
 
 namespace mst {
 
-constexpr int kModeMel = 4;           // internal epilogue id (after the public MST_OUT_* ids 0..3)
+constexpr int kModeSplit = 4;         // internal epilogue: |S|^2 as split bf16 (hi, lo) rows for the tensor-core mel projection
 constexpr int kTileStride = 1028;     // floats per frame row of the bin-major staging tile (== 4 mod 32: conflict-free)
 
-struct MelDev {            // device view of a mel plan (banded-compact filterbank)
-  const float* w;          // compact weights, row m starts at woff[m]
-  const int32_t* klo;      // first non-zero bin of row m
-  const int32_t* kcnt;     // number of bins in the band of row m
-  const int32_t* woff;
-  int n_mels;
-  int apply_log1p;
+struct SplitOut {          // ring of split-precision power-spectrum rows (kSpecPad bf16 each), consumed by mel_gemm.cu
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+  int64_t g0;              // global frame id stored in ring row 0
 };
 
 // Load one frame (centre-padded, reflect or zero) as z[m] = x[2m] + i*x[2m+1], m = 32*r + lane, times the window.
@@ -71,7 +69,8 @@ constexpr size_t kStftSmemBytes = 8192 + sizeof(float2) * kTwpCount + 8192 + siz
 template <int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips, const int32_t* __restrict__ tile_clip,
-            int total_tiles, int hop, int pad_mode, Tables tabs, int layout, void* __restrict__ out_v, MelDev mel) {
+            int tile_begin, int tile_end, int hop, int pad_mode, Tables tabs, int layout, void* __restrict__ out_v,
+            SplitOut split) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s_tw1024 = reinterpret_cast<float2*>(smem_raw);
   float2* s_twp = s_tw1024 + 1024;
@@ -87,9 +86,9 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
   stage_table(s_window, tabs.window, 512);
   __syncthreads();
 
-  const int n_out = (MODE == kModeMel) ? mel.n_mels : kBins;  // values per frame in the output
+  const int n_out = kBins;  // values per frame in the output
 
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (int tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
     const int c = __ldg(tile_clip + tile);
     const ClipDesc cd = clips[c];
     const int t0 = (tile - cd.tile_offset) * kWarpsPerCta;
@@ -97,7 +96,7 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
     const bool active = t < cd.frames;
     {  // pull the audio of this CTA's next tile towards L2 while this one computes
       const int nt = tile + gridDim.x;
-      if (nt < total_tiles && warp == 0) {
+      if (nt < tile_end && warp == 0) {
         const int c2 = __ldg(tile_clip + nt);
         const ClipDesc cn = clips[c2];
         const int64_t b0 = (int64_t)(nt - cn.tile_offset) * kWarpsPerCta * hop - kHalf;
@@ -129,48 +128,45 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
 
     // real-valued epilogues ------------------------------------------------------------------
     float* out = reinterpret_cast<float*>(out_v);
-    if (MODE == kModeMel) {
-      // power spectrum of this frame -> this warp's scratch (linear [k]), then banded mel rows per lane
-      float* pw = reinterpret_cast<float*>(scratch);
+    if (MODE == kModeSplit) {
+      // |S|^2 -> (hi, lo) bf16 rows staged in this warp's scratch, then copied out with 128-bit stores
+      __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(scratch);
+      __nv_bfloat16* sl = sh + kSpecPad;
       __syncwarp();
       if (active) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pw[mirror_bin(lane, kb, j)] = fmaf(o[j].x, o[j].x, o[j].y * o[j].y);
-        if (lane == 0) pw[512] = fmaf(mid.x, mid.x, mid.y * mid.y);
-      }
-      __syncwarp();
-      float melv[8];  // n_mels <= 256
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        melv[i] = 0.0f;
-        const int m = lane + 32 * i;
-        if (active && m < mel.n_mels) {
-          const int k0 = __ldg(mel.klo + m), cnt = __ldg(mel.kcnt + m);
-          const float* wr = mel.w + __ldg(mel.woff + m);
-          float acc = 0.0f;
-          for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(wr + j), pw[k0 + j], acc);
-          melv[i] = mel.apply_log1p ? fast_log1p(acc) : acc;
+        for (int j = 0; j < 32; ++j) {
+          const float p = fmaf(o[j].x, o[j].x, o[j].y * o[j].y);
+          const __nv_bfloat16 h = __float2bfloat16_rn(p);
+          const int k = mirror_bin(lane, kb, j);
+          sh[k] = h;
+          sl[k] = __float2bfloat16_rn(p - __bfloat162float(h));
+        }
+        if (lane == 0) {
+          const float p = fmaf(mid.x, mid.x, mid.y * mid.y);
+          const __nv_bfloat16 h = __float2bfloat16_rn(p);
+          sh[512] = h;
+          sl[512] = __float2bfloat16_rn(p - __bfloat162float(h));
+        }
+        for (int k = kBins + lane; k < kSpecPad; k += 32) {  // zero padding of the last K-slice
+          sh[k] = __float2bfloat16_rn(0.0f);
+          sl[k] = __float2bfloat16_rn(0.0f);
         }
       }
       __syncwarp();
-      if (layout == MST_LAYOUT_FRAME_MAJOR) {
-        if (active) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = lane + 32 * i;
-            if (m < mel.n_mels) out[g * mel.n_mels + m] = melv[i];
-          }
-        }
-      } else {
-        __syncthreads();  // every warp is done with its scratch before the tile overwrites it
-        if (active) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = lane + 32 * i;
-            if (m < mel.n_mels) s_tile[warp * kTileStride + m] = melv[i];
-          }
+      if (active) {
+        const int64_t r = g - split.g0;
+        uint4* dh = reinterpret_cast<uint4*>(split.hi + r * kSpecPad);
+        uint4* dl = reinterpret_cast<uint4*>(split.lo + r * kSpecPad);
+        const uint4* s4h = reinterpret_cast<const uint4*>(sh);
+        const uint4* s4l = reinterpret_cast<const uint4*>(sl);
+        for (int i = lane; i < kSpecPad / 8; i += 32) {
+          dh[i] = s4h[i];
+          dl[i] = s4l[i];
         }
       }
+      __syncwarp();
+      continue;
     } else {
       if (layout == MST_LAYOUT_FRAME_MAJOR) {
         if (active) {
@@ -203,8 +199,8 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
 }
 
 template <int MODE>
-static int launch_stft(const float* d_audio, const mst_batch* b, int layout, void* d_out, const MelDev& mel,
-                       cudaStream_t stream) {
+static int launch_stft(const float* d_audio, const mst_batch* b, int layout, void* d_out, const SplitOut& split,
+                       int tile_begin, int tile_end, cudaStream_t stream) {
   Tables tabs;
   int rc = get_tables(&tabs);
   if (rc) return rc;
@@ -218,9 +214,9 @@ static int launch_stft(const float* d_audio, const mst_batch* b, int layout, voi
   }
   int sms = 0;
   MST_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = std::min(b->total_tiles, 2 * sms);
-  stft_kernel<MODE><<<grid, kWarpsPerCta * 32, smem, stream>>>(d_audio, b->d_clips, b->d_tile_clip, b->total_tiles,
-                                                              b->hop, b->pad_mode, tabs, layout, d_out, mel);
+  const int grid = std::min(tile_end - tile_begin, 2 * sms);
+  stft_kernel<MODE><<<grid, kWarpsPerCta * 32, smem, stream>>>(d_audio, b->d_clips, b->d_tile_clip, tile_begin, tile_end,
+                                                              b->hop, b->pad_mode, tabs, layout, d_out, split);
   MST_CUDA_OK(cudaGetLastError());
   count_launch();
   return MST_OK;
@@ -230,29 +226,23 @@ static int launch_stft(const float* d_audio, const mst_batch* b, int layout, voi
 
 using namespace mst;
 
-struct mst_mel_plan {
-  int n_mels = 0, n_bins = 0;
-  float* d_w = nullptr;      // compact band weights
-  int32_t* d_meta = nullptr; // klo[n_mels], kcnt[n_mels], woff[n_mels]
-  float* d_dense = nullptr;  // dense [n_mels][n_bins] copy (kept for later tensor-core forms)
-};
-
 extern "C" {
 
 int mst_stft_f32(const float* d_audio, const mst_batch_t* b, int out_mode, int layout, void* d_out,
                  mst_stream_t stream) {
   if (!d_audio || !b || !d_out) return fail(MST_ERR_INVALID, "mst_stft_f32: null argument");
   if (layout != MST_LAYOUT_FRAME_MAJOR && layout != MST_LAYOUT_BIN_MAJOR) return fail(MST_ERR_INVALID, "bad layout %d", layout);
-  MelDev none{};
+  SplitOut none{};
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int nt = b->total_tiles;
   switch (out_mode) {
     case MST_OUT_COMPLEX:
       if (layout != MST_LAYOUT_FRAME_MAJOR)
         return fail(MST_ERR_UNSUPPORTED, "complex STFT output is frame-major only (librosa's native Fortran order)");
-      return launch_stft<MST_OUT_COMPLEX>(d_audio, b, layout, d_out, none, s);
-    case MST_OUT_MAGNITUDE: return launch_stft<MST_OUT_MAGNITUDE>(d_audio, b, layout, d_out, none, s);
-    case MST_OUT_POWER: return launch_stft<MST_OUT_POWER>(d_audio, b, layout, d_out, none, s);
-    case MST_OUT_LOG1P_POWER: return launch_stft<MST_OUT_LOG1P_POWER>(d_audio, b, layout, d_out, none, s);
+      return launch_stft<MST_OUT_COMPLEX>(d_audio, b, layout, d_out, none, 0, nt, s);
+    case MST_OUT_MAGNITUDE: return launch_stft<MST_OUT_MAGNITUDE>(d_audio, b, layout, d_out, none, 0, nt, s);
+    case MST_OUT_POWER: return launch_stft<MST_OUT_POWER>(d_audio, b, layout, d_out, none, 0, nt, s);
+    case MST_OUT_LOG1P_POWER: return launch_stft<MST_OUT_LOG1P_POWER>(d_audio, b, layout, d_out, none, 0, nt, s);
     default: return fail(MST_ERR_INVALID, "bad out_mode %d", out_mode);
   }
 }
@@ -262,28 +252,41 @@ int mst_mel_plan_create(const float* W, int n_mels, int n_bins, mst_mel_plan_t**
   *out = nullptr;
   if (n_bins != kBins) return fail(MST_ERR_UNSUPPORTED, "mel plan needs n_bins=1025 (n_fft=2048), got %d", n_bins);
   if (n_mels < 1 || n_mels > 256) return fail(MST_ERR_UNSUPPORTED, "n_mels=%d outside [1,256]", n_mels);
-  std::vector<int32_t> meta((size_t)3 * n_mels);
-  std::vector<float> compact;
-  for (int m = 0; m < n_mels; ++m) {
-    int lo = n_bins, hi = -1;
-    for (int k = 0; k < n_bins; ++k)
-      if (W[(size_t)m * n_bins + k] != 0.0f) { lo = std::min(lo, k); hi = std::max(hi, k); }
-    const int cnt = hi >= lo ? hi - lo + 1 : 0;
-    meta[m] = cnt ? lo : 0;
-    meta[n_mels + m] = cnt;
-    meta[2 * n_mels + m] = (int32_t)compact.size();
-    for (int k = 0; k < cnt; ++k) compact.push_back(W[(size_t)m * n_bins + lo + k]);
-  }
   mst_mel_plan* p = new mst_mel_plan();
   p->n_mels = n_mels; p->n_bins = n_bins;
-  if (cudaMalloc(&p->d_w, sizeof(float) * std::max<size_t>(1, compact.size())) != cudaSuccess ||
-      cudaMalloc(&p->d_meta, sizeof(int32_t) * meta.size()) != cudaSuccess ||
-      cudaMalloc(&p->d_dense, sizeof(float) * (size_t)n_mels * n_bins) != cudaSuccess ||
-      cudaMemcpy(p->d_w, compact.data(), sizeof(float) * compact.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(p->d_meta, meta.data(), sizeof(int32_t) * meta.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(p->d_dense, W, sizeof(float) * (size_t)n_mels * n_bins, cudaMemcpyHostToDevice) != cudaSuccess) {
+  // band of non-zero mel rows per 64-bin K-slice, padded to multiples of 16 rows (UMMA N granularity at M=128)
+  std::vector<__nv_bfloat16> hi, lo;
+  p->slices.n_slices = kMaxSlices;
+  for (int s = 0; s < kMaxSlices; ++s) {
+    int lo_m = n_mels, hi_m = -1;
+    for (int m = 0; m < n_mels; ++m)
+      for (int k = 64 * s; k < std::min(64 * s + 64, n_bins); ++k)
+        if (W[(size_t)m * n_bins + k] != 0.0f) { lo_m = std::min(lo_m, m); hi_m = std::max(hi_m, m); }
+    p->slices.row[s] = (int)(hi.size() / 64);
+    if (hi_m < 0) { p->slices.n0[s] = 0; p->slices.n[s] = 0; continue; }
+    const int n0 = (lo_m / 16) * 16, n1 = (hi_m / 16 + 1) * 16;
+    p->slices.n0[s] = n0; p->slices.n[s] = n1 - n0;
+    for (int m = n0; m < n1; ++m)
+      for (int k = 64 * s; k < 64 * s + 64; ++k) {
+        const float w = (m < n_mels && k < n_bins) ? W[(size_t)m * n_bins + k] : 0.0f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        hi.push_back(h);
+        lo.push_back(__float2bfloat16_rn(w - __bfloat162float(h)));
+      }
+  }
+  p->w_rows = (int)(hi.size() / 64);
+  const size_t band_bytes = std::max<size_t>(1, hi.size()) * sizeof(__nv_bfloat16);
+  if (cudaMalloc(&p->d_dense, sizeof(float) * (size_t)n_mels * n_bins) != cudaSuccess ||
+      cudaMalloc(&p->d_band_hi, band_bytes) != cudaSuccess || cudaMalloc(&p->d_band_lo, band_bytes) != cudaSuccess ||
+      cudaMemcpy(p->d_dense, W, sizeof(float) * (size_t)n_mels * n_bins, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(p->d_band_hi, hi.data(), hi.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(p->d_band_lo, lo.data(), lo.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice) != cudaSuccess) {
     mst_mel_plan_destroy(p);
     return fail(MST_ERR_CUDA, "mel plan upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (mel_gemm_smem_bytes(p) > 227 * 1024) {
+    mst_mel_plan_destroy(p);
+    return fail(MST_ERR_UNSUPPORTED, "banded filterbank (%d rows) does not fit in shared memory", p->w_rows);
   }
   *out = p;
   return MST_OK;
@@ -291,26 +294,55 @@ int mst_mel_plan_create(const float* W, int n_mels, int n_bins, mst_mel_plan_t**
 
 void mst_mel_plan_destroy(mst_mel_plan_t* p) {
   if (!p) return;
-  if (p->d_w) cudaFree(p->d_w);
-  if (p->d_meta) cudaFree(p->d_meta);
   if (p->d_dense) cudaFree(p->d_dense);
+  if (p->d_band_hi) cudaFree(p->d_band_hi);
+  if (p->d_band_lo) cudaFree(p->d_band_lo);
   delete p;
 }
 
-size_t mst_stft_mel_workspace_bytes(const mst_batch_t*, const mst_mel_plan_t*) { return 0; }
+// Ring of split-precision power-spectrum rows between the STFT kernel and the projection kernel: one full wave of
+// 128-frame projection tiles (n_SM x 128 rows x 2 x 2176 B ~ 82 MB on B200), sized to stay resident in the 126 MB L2.
+static int64_t ring_rows_for_device() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (int64_t)sms * 128;
+}
+
+size_t mst_stft_mel_workspace_bytes(const mst_batch_t*, const mst_mel_plan_t*) {
+  return 2 * (size_t)ring_rows_for_device() * kSpecPad * sizeof(__nv_bfloat16) + 1024;
+}
 
 int mst_stft_mel_f32(const float* d_audio, const mst_batch_t* b, const mst_mel_plan_t* plan, int apply_log1p, int layout,
-                     float* d_out, void*, size_t, mst_stream_t stream) {
-  if (!d_audio || !b || !plan || !d_out) return fail(MST_ERR_INVALID, "mst_stft_mel_f32: null argument");
+                     float* d_out, void* d_workspace, size_t workspace_bytes, mst_stream_t stream) {
+  if (!d_audio || !b || !plan || !d_out || !d_workspace) return fail(MST_ERR_INVALID, "mst_stft_mel_f32: null argument");
   if (layout != MST_LAYOUT_FRAME_MAJOR && layout != MST_LAYOUT_BIN_MAJOR) return fail(MST_ERR_INVALID, "bad layout %d", layout);
-  MelDev mel;
-  mel.w = plan->d_w;
-  mel.klo = plan->d_meta;
-  mel.kcnt = plan->d_meta + plan->n_mels;
-  mel.woff = plan->d_meta + 2 * plan->n_mels;
-  mel.n_mels = plan->n_mels;
-  mel.apply_log1p = apply_log1p;
-  return launch_stft<kModeMel>(d_audio, b, layout, d_out, mel, reinterpret_cast<cudaStream_t>(stream));
+  if (workspace_bytes < mst_stft_mel_workspace_bytes(b, plan))
+    return fail(MST_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, mst_stft_mel_workspace_bytes(b, plan));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t ring_rows = ring_rows_for_device();
+  char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_workspace) + 1023) & ~(uintptr_t)1023);
+  SplitOut split;
+  split.hi = reinterpret_cast<__nv_bfloat16*>(ws);
+  split.lo = split.hi + ring_rows * kSpecPad;
+  const int chunk_tiles = (int)(ring_rows / kWarpsPerCta);  // a tile holds at most 8 frames
+  int c = 0;                                                // clip cursor (tiles are ordered by clip)
+  for (int tile0 = 0; tile0 < b->total_tiles; tile0 += chunk_tiles) {
+    const int tile1 = std::min(b->total_tiles, tile0 + chunk_tiles);
+    while (c + 1 < b->n_clips && b->h_clips[c + 1].tile_offset <= tile0) ++c;
+    const int64_t g0 = b->h_clips[c].frame_offset + (int64_t)(tile0 - b->h_clips[c].tile_offset) * kWarpsPerCta;
+    int64_t g1 = b->total_frames;
+    if (tile1 < b->total_tiles) {
+      int c1 = c;
+      while (c1 + 1 < b->n_clips && b->h_clips[c1 + 1].tile_offset <= tile1) ++c1;
+      g1 = b->h_clips[c1].frame_offset + (int64_t)(tile1 - b->h_clips[c1].tile_offset) * kWarpsPerCta;
+    }
+    split.g0 = g0;
+    int rc = launch_stft<kModeSplit>(d_audio, b, layout, nullptr, split, tile0, tile1, s);
+    if (rc) return rc;
+    rc = launch_mel_gemm(plan, b, split.hi, split.lo, ring_rows, (int)(g1 - g0), g0, apply_log1p, layout, d_out, s);
+    if (rc) return rc;
+  }
+  return MST_OK;
 }
 
 }  // extern "C"
