@@ -136,6 +136,30 @@ def test_mel_frame_major_batch(pkg, gpu):
         assert_close(got[c].T, omel.logmel(y[c * 88200:(c + 1) * 88200], 22050, 2048, 512).astype(np.float64))
 
 
+def test_mel_multi_chunk_ragged_and_80_mels(pkg, gpu):
+    """More frames than one ring chunk (148 x 128 rows), ragged clips, frame tiles straddling projection tiles,
+    and a filterbank with a different band structure (80 mels)."""
+    F = pkg.features
+    lens = [88200, 30001, 2049, 66150] * 60  # 240 clips, 22k frames > 18 944
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    y = clip(23, int(sum(lens)), "noise")
+    a = torch.from_numpy(y).to(gpu)
+    b = F.ClipBatch.from_clips(offs, lens, 512, device=gpu)
+    assert b.total_frames > 148 * 128
+    for n_mels in (128, 80):
+        plan = F.MelPlan.get(22050, n_mels=n_mels, device=gpu)
+        bm = F.melspectrogram_batch(a, b, plan, log1p=False, layout=F.BIN_MAJOR).cpu().numpy()
+        fm = F.melspectrogram_batch(a, b, plan, log1p=True, layout=F.FRAME_MAJOR).view(-1, n_mels).cpu().numpy()
+        f0 = 0
+        for i, (o, l) in enumerate(zip(offs, lens)):
+            T = 1 + l // 512
+            if i in (0, 1, 2, 3, 119, 120, 203, 204, 205, 206, 207, 208, 239):  # includes the clips around the chunk boundary
+                ref = omel.melspectrogram(y[o:o + l], 22050, 2048, 512, n_mels).astype(np.float64)
+                assert_close(bm[f0 * n_mels:(f0 + T) * n_mels].reshape(n_mels, T), ref)
+                assert_close(fm[f0:f0 + T].T, np.log1p(ref))
+            f0 += T
+
+
 # ---- P3: piano roll (bit-exact) -------------------------------------------------------------
 def test_pianoroll_known_answer(pkg):
     roll, onoff = pkg.preprocess.notes_to_pianoroll([60, 60, 64, 21], [100, 90, 80, 1], [0, 0.5, 0.25, 0.999],
