@@ -71,26 +71,41 @@ __device__ __forceinline__ void synthesize_frame(float2 (&y)[32], float2 mid, fl
   }
 }
 
+constexpr int kSlot = 2 * kScratchPerWarp;  // floats between consecutive frame slots
+
+// Overlap-add of one tile when hop divides n_fft (R = n_fft / hop frames overlap every sample): thread j walks the
+// span hop-block by hop-block; block b receives frames f = b-R+1 .. b, summed in increasing f.
+template <int R>
+__device__ __forceinline__ void ola_blocks(const float* s_slots, int nvalid, int hop, int hop_shift, float* dst) {
+  const int n_blocks = nvalid - 1 + R;
+  for (int j = threadIdx.x; j < hop; j += blockDim.x) {
+    const float* sp = s_slots + j;
+    float* dp = dst + j;
+    for (int b = 0; b < n_blocks; ++b) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int r = R - 1; r >= 0; --r) {
+        const int f = b - r;
+        if (f >= 0 && f < nvalid) sum += sp[f * kSlot + (r << hop_shift)];
+      }
+      atomicAdd(dp + (b << hop_shift), sum);
+    }
+  }
+}
+
 // Sum the tile's frame slots in frame order and add the span to the global accumulator; zero the next accumulator.
-// When hop divides n_fft the span is walked hop-block by hop-block: block b of the span receives frames
-// f = b-R+1 .. b (R = n_fft / hop), bounds that are uniform across the CTA, so the inner loop has no divergence and no
-// divisions.  Other hops use a generic per-sample form.
 __device__ __forceinline__ void overlap_add_tile(const float* s_slots, const ClipDesc& cd, int t0, int hop, int hop_shift,
                                                  float* __restrict__ acc_out, float* __restrict__ acc_zero) {
   const int nvalid = min(kWarpsPerCta, cd.frames - t0);
   float* dst = acc_out + cd.acc_offset + (int64_t)t0 * hop;
-  constexpr int kSlot = 2 * kScratchPerWarp;  // floats between consecutive frame slots
-  if (hop_shift >= 0) {
-    const int R = kNfft >> hop_shift;
-    const int n_blocks = nvalid - 1 + R;
-    for (int b = 0; b < n_blocks; ++b) {
-      const int f_lo = max(0, b - R + 1), f_hi = min(b, nvalid - 1);
-      for (int j = threadIdx.x; j < hop; j += blockDim.x) {
-        float sum = 0.0f;
-        for (int f = f_lo; f <= f_hi; ++f) sum += s_slots[f * kSlot + ((b - f) << hop_shift) + j];
-        atomicAdd(dst + (b << hop_shift) + j, sum);
-      }
-    }
+  if (hop_shift == 9) {
+    ola_blocks<4>(s_slots, nvalid, hop, hop_shift, dst);
+  } else if (hop_shift == 8) {
+    ola_blocks<8>(s_slots, nvalid, hop, hop_shift, dst);
+  } else if (hop_shift == 10) {
+    ola_blocks<2>(s_slots, nvalid, hop, hop_shift, dst);
+  } else if (hop_shift == 7) {
+    ola_blocks<16>(s_slots, nvalid, hop, hop_shift, dst);
   } else {
     const int span = (nvalid - 1) * hop + kNfft;
     for (int p = threadIdx.x; p < span; p += blockDim.x) {
@@ -108,7 +123,12 @@ __device__ __forceinline__ void overlap_add_tile(const float* s_slots, const Cli
     const bool last = t0 + kWarpsPerCta >= cd.frames;
     const int64_t z1 = last ? acc_len : z0 + (int64_t)kWarpsPerCta * hop;
     float* z = acc_zero + cd.acc_offset;
-    for (int64_t p = z0 + threadIdx.x; p < z1; p += blockDim.x) z[p] = 0.0f;
+    if (((z0 | z1) & 3) == 0) {  // accumulators are 16-byte aligned per clip
+      float4* z4 = reinterpret_cast<float4*>(z);
+      for (int64_t p = (z0 >> 2) + threadIdx.x; p < (z1 >> 2); p += blockDim.x) z4[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int64_t p = z0 + threadIdx.x; p < z1; p += blockDim.x) z[p] = 0.0f;
+    }
   }
 }
 

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict_
   const bool simple = (int64_t)fs * EPV <= sr;                // at most one column crossing per vector
   const unsigned fs_magic = (unsigned)(0x100000000ull / (unsigned)fs) + 1u;  // exact ceil-div by fs for numerators < 2^32/fs
   const int step_col = (32 * EPV * fs) / sr, step_rem = (32 * EPV * fs) % sr;  // advance of 32 vectors
+  const bool staged = simple && ((int64_t)32 * kUpVec * EPV * fs) / sr + 2 <= 62;  // chunk fits 64 staged columns
   for (int piece = blockIdx.z; piece < n_pieces; piece += gridDim.z) {
     const int64_t r0 = row_off[piece], T = row_off[piece + 1] - r0;
     const int64_t N = samp_off[piece + 1] - samp_off[piece];
@@ -161,6 +162,31 @@ __global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict_
         const int64_t prod = (head + v * EPV) * fs;
         int64_t col = prod / sr;
         int rem = (int)(prod - col * sr);
+        if (staged) {
+          // The chunk spans fewer than 62 roll columns: fetch them once (two bytes per lane) and serve every vector's
+          // current / next column value by warp shuffle -- no dependent global loads inside the store loop.
+          const int64_t c0 = __shfl_sync(0xffffffffu, col, 0);
+          const int8_t b0 = c0 + lane < T ? src[(c0 + lane) * 128] : (int8_t)0;
+          const int8_t b1 = c0 + 32 + lane < T ? src[(c0 + 32 + lane) * 128] : (int8_t)0;
+#pragma unroll
+          for (int u = 0; u < kUpVec; ++u) {
+            int rel = (int)(col - c0);
+            rel = rel < 0 ? 0 : (rel > 62 ? 62 : rel);
+            const int lo0 = __shfl_sync(0xffffffffu, (int)b0, rel & 31), hi0 = __shfl_sync(0xffffffffu, (int)b1, rel & 31);
+            const int lo1 = __shfl_sync(0xffffffffu, (int)b0, (rel + 1) & 31), hi1 = __shfl_sync(0xffffffffu, (int)b1, (rel + 1) & 31);
+            const int8_t cur = (int8_t)(rel < 32 ? lo0 : hi0);
+            const int8_t nxt = (int8_t)(rel + 1 < 32 ? lo1 : hi1);
+            OUT vals[EPV];
+            const int e_cross = (int)__umulhi((unsigned)(sr - rem + fs - 1), fs_magic);
+            make_vector<OUT>(vals, cur, nxt, e_cross);
+            if (v < nvec) *reinterpret_cast<uint4*>(row + head + v * EPV) = *reinterpret_cast<const uint4*>(vals);
+            v += 32;
+            col += step_col;
+            rem += step_rem;
+            if (rem >= sr) { rem -= sr; ++col; }
+          }
+          continue;
+        }
 #pragma unroll
         for (int u = 0; u < kUpVec; ++u) {
           if (v >= nvec) break;
