@@ -215,6 +215,13 @@ def run_ours(args):
     launches = pkg._lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
+    # reference point for the write-only stage: what a plain device fill achieves on this GPU (measured live)
+    fill_buf = torch.empty(2 * 1024 ** 3, dtype=torch.int8, device=device)
+    fill_buf.fill_(1)
+    fill_ms = float(np.median(timed(lambda: fill_buf.fill_(1), 5)))
+    write_peak = fill_buf.numel() / (fill_ms * 1e-3) / 1e9
+    del fill_buf
+
     # kernel-level roofline of the dominant kernel (Griffin-Lim iteration): (t[32 iters] - t[0 iters]) / 32
     t0 = float(np.median(timed(lambda: stage_c(0), 3)))
     t32 = float(np.median(tc))
@@ -246,11 +253,17 @@ def run_ours(args):
             "stft_logmel": {"ms": ma, "audio_s_per_s": world * audio_seconds / (ma * 1e-3),
                             "hbm_frac": a_bytes / (ma * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": a_bytes},
             "pianoroll_upsample": {"ms": mb, "audio_s_per_s": world * audio_seconds / (mb * 1e-3),
-                                   "hbm_frac": b_bytes / (mb * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": b_bytes},
+                                   "hbm_frac": b_bytes / (mb * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": b_bytes,
+                                   "write_only_peak_gbs": write_peak, "write_only_frac": b_bytes / (mb * 1e-3) / 1e9 / write_peak},
             "griffinlim32": {"ms": mc, "audio_s_per_s": world * audio_seconds / (mc * 1e-3),
                              "hbm_frac": gl_total_bytes / (mc * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": gl_total_bytes},
         }
         achieved = gl_iter_bytes / (iter_ms * 1e-3) / 1e9
+        traffic = args.traffic
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if traffic is None and os.path.exists(tpath):
+            with open(tpath) as f:  # ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of one GL iteration
+                traffic = json.load(f)["gl_iteration_dram_bytes_per_clip"] * n_clips
         line = {
             "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -262,7 +275,7 @@ def run_ours(args):
             "stages": stages,
             "roofline": {"bound": "hbm", "kernel": "gl_kernel<false> (one Griffin-Lim iteration)", "achieved": achieved,
                          "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "ms_per_launch": iter_ms, "algorithmic_bytes_per_launch": gl_iter_bytes, "traffic": args.traffic},
+                         "ms_per_launch": iter_ms, "algorithmic_bytes_per_launch": gl_iter_bytes, "traffic": traffic},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall_s,
         }
         if e2e is not None:
