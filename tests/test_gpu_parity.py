@@ -246,6 +246,47 @@ def test_griffinlim_spectral_convergence(pkg, hop, n_iter, mom):
     assert sc_got < 0.5
 
 
+def test_griffinlim_reference_configuration_300_iterations(pkg):
+    """The reference's own call: n_iter=300, hop 256 (inference.py:105, tests/test_griffinlim.py:23)."""
+    y = clip(35, 22050)
+    S = np.abs(ostft.stft(y, 2048, 256)).astype(np.float32)
+    u = ogl.random_phase(S.shape, 3)
+    ref = ogl.griffinlim(S, 300, 256, init_phase=u)
+    got = pkg.features.griffinlim(S, n_iter=300, hop_length=256, init_phase=u)
+    sc_ref, sc_got = _sc(S, ref, 256), _sc(S, got, 256)
+    assert abs(sc_ref - sc_got) <= 1e-3, (sc_ref, sc_got)
+    # random_state=int reproduces librosa's RandomState(seed).rand(*S.shape) phase draw
+    got2 = pkg.features.griffinlim(S, n_iter=8, hop_length=256, random_state=3)
+    ref2 = ogl.griffinlim(S, 8, 256, init_phase=u)
+    assert rel_l2(got2, ref2.astype(np.float64)) < 5e-3
+
+
+def test_griffinlim_ragged_batch_matches_per_clip_oracle(pkg, gpu):
+    """Ragged batch in one launch sequence, bin-major log1p-power input (what the model emits), shared phases."""
+    F = pkg.features
+    frames = [60, 173, 45]
+    hop = 512
+    S_list, u_list = [], []
+    for i, T in enumerate(frames):
+        yy = clip(40 + i, hop * (T - 1))
+        S_list.append(np.abs(ostft.stft(yy, 2048, hop)).astype(np.float32))
+        u_list.append(ogl.random_phase(S_list[-1].shape, 10 + i).astype(np.float32))
+        assert S_list[-1].shape == (1025, T)
+    logp = np.concatenate([np.log1p(S.astype(np.float64) ** 2).astype(np.float32).ravel() for S in S_list])
+    ph = np.concatenate([u.ravel() for u in u_list])
+    gb = F.ClipBatch.from_frames(frames, hop, device=gpu)
+    out = F.griffinlim_batch(torch.from_numpy(logp).to(gpu), gb, n_iter=16, init_phase=torch.from_numpy(ph).to(gpu),
+                             layout=F.BIN_MAJOR, is_log1p_power=True).cpu().numpy()
+    o = 0
+    for S, u, T in zip(S_list, u_list, frames):
+        L = hop * (T - 1)
+        mag = ogl.logpower_to_magnitude(np.log1p(S.astype(np.float64) ** 2).astype(np.float32))
+        ref = ogl.griffinlim(mag, 16, hop, init_phase=u)
+        assert abs(_sc(mag, ref, hop) - _sc(mag, out[o:o + L], hop)) <= 1e-3
+        o += L
+    assert o == out.shape[0]
+
+
 def test_griffinlim_early_iterations_match_waveform(pkg):
     """Before the chaotic phase dynamics amplify float32 rounding, the waveform itself must agree."""
     y = clip(32, 30000)
