@@ -156,6 +156,16 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
                        int n_iter, float momentum, const float* d_init_phase, int init_mode, uint64_t seed,
                        float* d_y_out, void* d_workspace, size_t workspace_bytes, mst_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * "Next" row: the resampling half of librosa.load(path, sr=hp.sr)
+ * [preprocess.py:106, model/inference.py:54, tests/test_griffinlim.py:16] = resampy 'kaiser_best'
+ * (64 zero crossings, Kaiser beta 14.7697, roll-off 0.9476, 512-per-crossing table, linear interpolation).
+ * mst_resample_length = ceil(n_in * sr_out / sr_in) (librosa pads resampy's floor() length with zeros).
+ * d_out must hold mst_resample_length(...) floats.
+ * ------------------------------------------------------------------------------------------- */
+int64_t mst_resample_length(int64_t n_in, int sr_in, int sr_out);
+int mst_resample_f32(const float* d_in, int64_t n_in, int sr_in, int sr_out, float* d_out, mst_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

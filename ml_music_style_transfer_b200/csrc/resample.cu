@@ -1,0 +1,142 @@
+// "Next" row 1: the resampling half of librosa.load(path, sr=hp.sr)
+// (reference preprocessing/preprocess.py:106, model/inference.py:54, tests/test_griffinlim.py:16).
+// Band-limited sinc interpolation exactly as resampy 0.2.2 'kaiser_best' evaluates it (librosa 0.8's default
+// res_type): half-window rolloff*sinc(rolloff*t)*kaiser(beta) tabulated 512 times per zero crossing over 64 zero
+// crossings, linear interpolation between table entries, left wing then right wing.  One thread per output sample;
+// the 256 KB (value, delta) table is L2 resident.  Index arithmetic is done in double so that table offsets match
+// the Python evaluation bit for bit.
+#include <math.h>
+#include <map>
+#include <mutex>
+#include <vector>
+#include "mst_common.cuh"
+
+namespace mst {
+
+constexpr int kRsZeros = 64, kRsPrecision = 9, kRsTable = 1 << kRsPrecision;  // 512 entries per zero crossing
+constexpr int kRsWin = kRsZeros * kRsTable + 1;                               // 32769
+constexpr double kRsBeta = 14.769656459379492, kRsRolloff = 0.9475937167399596;
+
+__global__ void resample_kernel(const float* __restrict__ x, int64_t n_in, float* __restrict__ y, int64_t n_out,
+                                int64_t n_fix, const float2* __restrict__ table, double time_increment, double scale,
+                                int index_step) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_fix; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t >= n_out) {  // librosa util.fix_length: zero padding up to ceil(n * ratio)
+      y[t] = 0.0f;
+      continue;
+    }
+    const double time_register = __dmul_rn((double)t, time_increment);
+    const int64_t n = (int64_t)time_register;
+    float acc = 0.0f;
+    // left wing
+    double frac = __dmul_rn(scale, time_register - (double)n);
+    double index_frac = __dmul_rn(frac, (double)kRsTable);
+    int offset = (int)index_frac;
+    float eta = (float)(index_frac - (double)offset);
+    int64_t lim = (kRsWin - offset) / index_step;
+    const int64_t i_max = n + 1 < lim ? n + 1 : lim;
+    for (int64_t i = 0; i < i_max; ++i) {
+      const float2 w = __ldg(table + offset + i * index_step);
+      acc = fmaf(fmaf(eta, w.y, w.x), __ldg(x + n - i), acc);
+    }
+    // right wing
+    frac = scale - frac;
+    index_frac = __dmul_rn(frac, (double)kRsTable);
+    offset = (int)index_frac;
+    eta = (float)(index_frac - (double)offset);
+    lim = (kRsWin - offset) / index_step;
+    const int64_t k_max = n_in - n - 1 < lim ? n_in - n - 1 : lim;
+    for (int64_t k = 0; k < k_max; ++k) {
+      const float2 w = __ldg(table + offset + k * index_step);
+      acc = fmaf(fmaf(eta, w.y, w.x), __ldg(x + n + k + 1), acc);
+    }
+    y[t] = acc;
+  }
+}
+
+static double bessel_i0(double x) {
+  // power series, converges fast for x <= ~15 (beta = 14.77)
+  double sum = 1.0, term = 1.0;
+  const double q = 0.25 * x * x;
+  for (int k = 1; k < 500; ++k) {
+    term *= q / ((double)k * (double)k);
+    sum += term;
+    if (term < 1e-18 * sum) break;
+  }
+  return sum;
+}
+
+static std::mutex g_rs_mutex;
+static std::map<std::tuple<int, int, int>, float2*> g_rs_tables;  // (device, sr_in, sr_out)
+
+static int get_rs_table(int sr_in, int sr_out, const float2** out) {
+  int dev = 0;
+  MST_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_rs_mutex);
+  auto key = std::make_tuple(dev, sr_in, sr_out);
+  auto it = g_rs_tables.find(key);
+  if (it == g_rs_tables.end()) {
+    const double ratio = (double)sr_out / (double)sr_in;
+    const int n = kRsWin - 1;
+    const double pi = 3.14159265358979323846, i0b = bessel_i0(kRsBeta);
+    std::vector<double> win((size_t)kRsWin);
+    for (int i = 0; i <= n; ++i) {
+      const double t = (i == n) ? (double)kRsZeros : (double)i * ((double)kRsZeros / (double)n);  // np.linspace
+      const double a = kRsRolloff * t;
+      const double sinc = a == 0.0 ? 1.0 : sin(pi * a) / (pi * a);
+      const double r = (double)i / (double)n;
+      const double arg = 1.0 - r * r;
+      const double taper = bessel_i0(kRsBeta * sqrt(arg > 0.0 ? arg : 0.0)) / i0b;
+      win[i] = taper * kRsRolloff * sinc;
+      if (ratio < 1.0) win[i] *= ratio;
+    }
+    std::vector<float2> tab((size_t)kRsWin);
+    for (int i = 0; i <= n; ++i) tab[i] = make_float2((float)win[i], i < n ? (float)(win[i + 1] - win[i]) : 0.0f);
+    float2* d = nullptr;
+    MST_CUDA_OK(cudaMalloc(&d, sizeof(float2) * tab.size()));
+    MST_CUDA_OK(cudaMemcpy(d, tab.data(), sizeof(float2) * tab.size(), cudaMemcpyHostToDevice));
+    it = g_rs_tables.emplace(key, d).first;
+  }
+  *out = it->second;
+  return MST_OK;
+}
+
+}  // namespace mst
+
+using namespace mst;
+
+extern "C" {
+
+int64_t mst_resample_length(int64_t n_in, int sr_in, int sr_out) {
+  if (n_in < 0 || sr_in <= 0 || sr_out <= 0) return -1;
+  if (sr_in == sr_out) return n_in;
+  return (int64_t)ceil((double)n_in * ((double)sr_out / (double)sr_in));
+}
+
+int mst_resample_f32(const float* d_in, int64_t n_in, int sr_in, int sr_out, float* d_out, mst_stream_t stream) {
+  if (!d_in || !d_out) return fail(MST_ERR_INVALID, "mst_resample_f32: null argument");
+  if (n_in <= 0 || sr_in <= 0 || sr_out <= 0) return fail(MST_ERR_INVALID, "mst_resample_f32: bad sizes");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (sr_in == sr_out) {
+    MST_CUDA_OK(cudaMemcpyAsync(d_out, d_in, sizeof(float) * (size_t)n_in, cudaMemcpyDeviceToDevice, s));
+    return MST_OK;
+  }
+  const double ratio = (double)sr_out / (double)sr_in;
+  const int64_t n_out = (int64_t)((double)n_in * ratio);
+  const int64_t n_fix = mst_resample_length(n_in, sr_in, sr_out);
+  const double scale = ratio < 1.0 ? ratio : 1.0;
+  const int index_step = (int)(scale * (double)kRsTable);
+  if (index_step < 1) return fail(MST_ERR_UNSUPPORTED, "down-sampling ratio %g too small", ratio);
+  const float2* table = nullptr;
+  int rc = get_rs_table(sr_in, sr_out, &table);
+  if (rc) return rc;
+  const int threads = 256;
+  const int64_t blocks = (n_fix + threads - 1) / threads;
+  resample_kernel<<<(unsigned)(blocks < 148 * 64 ? blocks : 148 * 64), threads, 0, s>>>(d_in, n_in, d_out, n_out, n_fix, table,
+                                                                                 1.0 / ratio, scale, index_step);
+  MST_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return MST_OK;
+}
+
+}  // extern "C"

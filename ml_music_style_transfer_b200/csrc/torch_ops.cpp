@@ -183,6 +183,18 @@ at::Tensor griffinlim(const at::Tensor& S, int64_t s_layout, bool s_is_log1p_pow
   return y;
 }
 
+at::Tensor resample(const at::Tensor& x, int64_t sr_in, int64_t sr_out) {
+  want(x, at::kFloat, "x");
+  TORCH_CHECK(x.dim() == 1, "resample expects a 1-D mono signal");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t n = mst_resample_length(x.numel(), (int)sr_in, (int)sr_out);
+  TORCH_CHECK(n >= 0, "bad resample arguments");
+  at::Tensor y = at::empty({n}, x.options());
+  check(mst_resample_f32(x.data_ptr<float>(), x.numel(), (int)sr_in, (int)sr_out, y.data_ptr<float>(), cur_stream()),
+        "mst_resample_f32");
+  return y;
+}
+
 }  // namespace
 
 TORCH_LIBRARY(mst_b200, m) {
@@ -206,6 +218,7 @@ TORCH_LIBRARY(mst_b200, m) {
   m.def("pianoroll_chunks(Tensor plane, int num_chunks, int chunk_rows, int stride_rows, int out_dtype) -> Tensor");
   m.def("pianoroll_upsample(Tensor plane, Tensor row_offsets, Tensor sample_offsets, int total_samples, int fs, int sr, "
         "int pitch_lo, int n_keys, int out_dtype) -> Tensor");
+  m.def("resample(Tensor x, int sr_in, int sr_out) -> Tensor");
   m.def("griffinlim(Tensor S, int s_layout, bool s_is_log1p_power, int batch, int n_iter, float momentum, "
         "Tensor? init_phase, int init_mode, int seed) -> Tensor");
 }
@@ -218,4 +231,5 @@ TORCH_LIBRARY_IMPL(mst_b200, CUDA, m) {
   m.impl("pianoroll_chunks", &pianoroll_chunks);
   m.impl("pianoroll_upsample", &pianoroll_upsample);
   m.impl("griffinlim", &griffinlim);
+  m.impl("resample", &resample);
 }

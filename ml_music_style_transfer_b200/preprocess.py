@@ -9,7 +9,7 @@ import glob
 import numpy as np
 import torch
 
-from . import _lib, features, pianoroll as _pr
+from . import _lib, audio_io, features, pianoroll as _pr
 from .midi import read_midi_notes
 
 
@@ -87,6 +87,20 @@ def process_pianoroll_into_chunks(pianoroll, onoff, song_id, num_chunks, debug=F
     if was_np:
         return score.cpu().numpy(), oo.cpu().numpy()
     return score, oo
+
+
+def load_audio(data_dir, song_id, style, debug=False):
+    """preprocess.py:99-115: glob the style's wav, librosa.load(path, sr=hp.sr) (decode, mono, kaiser_best resample)."""
+    audio_file = glob.glob(f"{data_dir}/{song_id}*{style}.wav")
+    if len(audio_file) == 0:
+        raise ValueError("couldnt find audio track!")
+    elif len(audio_file) > 1:
+        raise ValueError("multiple files picked up, issue:", audio_file)
+    y, sr = audio_io.load(audio_file[0], sr=hp.sr)
+    if debug is True:
+        print("length of audio clip / sr: ", len(y), sr)
+        print("audio files picked up:", audio_file)
+    return y
 
 
 def get_num_song_chunks(pianoroll, offset_percentage=0.1, max_chunks=100):

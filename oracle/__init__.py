@@ -19,4 +19,4 @@ that do exist in this image -- ``torch.stft`` / ``torch.istft``, ``scipy.signal.
 generated fixtures live in tests/golden/ together with the script that made them
 (tests/golden/make_golden.py).
 """
-from . import stft, mel, pianoroll, griffinlim, preprocess  # noqa: F401
+from . import stft, mel, pianoroll, griffinlim, preprocess, audio  # noqa: F401

@@ -45,6 +45,17 @@ def main():
         w = torchaudio.functional.griffinlim(torch.from_numpy(mag).double(), win, 2048, 512, 2048, 1.0, 8, mom, None, False)
         gl[f"y_iter8_mom{mom}"] = w.numpy().astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "griffinlim_torchaudio.npz"), **gl)
+    # resampling: torchaudio's sinc_interp_kaiser with the three 'kaiser_best' parameters (what torchaudio documents as
+    # the librosa-compatible configuration); independent of resampy's tabulated-window evaluation restated in oracle/
+    t = np.arange(16000) / 44100.0
+    x = (0.4 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 5000 * t + 1)
+         + 0.01 * np.random.default_rng(5).standard_normal(16000)).astype(np.float32)
+    rs = {"x": x}
+    for so, sn in ((44100, 22050), (48000, 44100), (22050, 44100)):
+        rs[f"y_{so}_{sn}"] = torchaudio.functional.resample(
+            torch.from_numpy(x).double(), so, sn, lowpass_filter_width=64, rolloff=0.9475937167399596,
+            resampling_method="sinc_interp_kaiser", beta=14.769656459379492).numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "resample_torchaudio.npz"), **rs)
     print("wrote", os.listdir(HERE))
 
 

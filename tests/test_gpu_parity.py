@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import griffinlim as ogl, mel as omel, pianoroll as opr, preprocess as opp, stft as ostft
+from oracle import audio as oaudio, griffinlim as ogl, mel as omel, pianoroll as opr, preprocess as opp, stft as ostft
 
 pytestmark = pytest.mark.gpu
 
@@ -226,6 +226,28 @@ def test_load_midi_dropin(pkg, tmp_path):
     assert np.array_equal(roll, ref_r) and np.array_equal(onoff, ref_o)
     with pytest.raises(ValueError):
         pkg.preprocess.load_midi(str(tmp_path), 9999)
+
+
+# ---- next row 1: librosa.load = WAV decode + mono + kaiser_best resample ------------------------------
+@pytest.mark.parametrize("so,sn", [(44100, 22050), (48000, 44100), (22050, 44100), (44100, 44100)])
+def test_resample_kaiser_best(pkg, so, sn):
+    x = clip(51, 30011, "noise") + clip(52, 30011)
+    got = pkg.audio_io.resample(x, so, sn)
+    ref = oaudio.resample(x, so, sn)
+    assert got.shape == ref.shape and got.dtype == np.float32
+    assert_close(got, ref.astype(np.float64))
+
+
+def test_load_audio_dropin(pkg, tmp_path):
+    """preprocess.py:99-115 on a stereo 48 kHz PCM16 file -> mono float32 at hp.sr = 44100."""
+    x = np.stack([clip(53, 24000), clip(54, 24000, "noise")], axis=1)
+    oaudio.write_wav(str(tmp_path / "2240_prelude_cuba.wav"), x, 48000, bits=16)
+    got = pkg.preprocess.load_audio(str(tmp_path), 2240, "cuba")
+    ref, sr = oaudio.load(str(tmp_path / "2240_prelude_cuba.wav"), sr=44100)
+    assert sr == 44100 and got.shape == ref.shape == (22050,) and got.dtype == np.float32
+    assert_close(got, ref.astype(np.float64))
+    with pytest.raises(ValueError):
+        pkg.preprocess.load_audio(str(tmp_path), 2240, "upright")
 
 
 # ---- P4: Griffin-Lim ------------------------------------------------------------------------

@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from oracle import griffinlim as ogl, mel as omel, pianoroll as opr, preprocess as opp, stft as ostft
+from oracle import audio as oaudio, griffinlim as ogl, mel as omel, pianoroll as opr, preprocess as opp, stft as ostft
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -157,6 +157,33 @@ def test_griffinlim_converges_and_inverse_map():
     p = (S ** 2)
     back = ogl.logpower_to_magnitude(np.log1p(p))
     assert np.allclose(back, S, rtol=2e-3, atol=1e-4)
+
+
+# ---- audio load (next row 1) -------------------------------------------------------------------
+@pytest.mark.parametrize("so,sn", [(44100, 22050), (48000, 44100), (22050, 44100)])
+def test_resample_matches_torchaudio_golden(so, sn):
+    g = np.load(os.path.join(GOLD, "resample_torchaudio.npz"))
+    y = oaudio.resample(g["x"], so, sn)
+    ref = g[f"y_{so}_{sn}"]
+    assert y.shape == ref.shape == (int(np.ceil(16000 * sn / so)),) and y.dtype == np.float32
+    # two different realisations of the same windowed-sinc filter: agree away from the (differently padded) edges
+    assert np.abs(y - ref)[2000:-2000].max() < 5e-4
+
+
+def test_wav_round_trip_and_load(tmp_path):
+    rng = np.random.default_rng(1)
+    x = (0.5 * rng.uniform(-1, 1, (3000, 2))).astype(np.float32)
+    for bits, tol in ((16, 1.0 / 32768), (24, 1.0 / (1 << 23)), (32, 0.0)):
+        p = str(tmp_path / f"a{bits}.wav")
+        oaudio.write_wav(p, x, 44100, bits=bits)
+        back, sr = oaudio.read_wav(p)
+        assert sr == 44100 and back.shape == x.shape and np.abs(back - x).max() <= tol
+        from ml_music_style_transfer_b200 import audio_io
+        back2, sr2 = audio_io.read_wav(p)  # the product's host decoder
+        assert sr2 == sr and np.array_equal(back, back2)
+    y, sr = oaudio.load(str(tmp_path / "a16.wav"), sr=22050)
+    assert sr == 22050 and y.shape == (1500,) and y.dtype == np.float32
+    assert oaudio.resample(x[:, 0], 44100, 44100) is not None and oaudio.resample(x[:, 0], 44100, 44100).shape == (3000,)
 
 
 # ---- host logic --------------------------------------------------------------------------------
