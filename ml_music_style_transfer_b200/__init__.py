@@ -9,6 +9,6 @@
 Everything computes in hand-written CUDA kernels behind ``torch.ops.mst_b200`` (C ABI: include/mst_b200.h).
 There is no CPU fallback.
 """
-from . import _lib, audio_io, features, pianoroll, preprocess, inference, sharding, midi  # noqa: F401
+from . import _lib, audio_io, dataset, features, pianoroll, preprocess, inference, sharding, midi  # noqa: F401
 
-__all__ = ["audio_io", "features", "pianoroll", "preprocess", "inference", "sharding", "midi"]
+__all__ = ["audio_io", "dataset", "features", "pianoroll", "preprocess", "inference", "sharding", "midi"]

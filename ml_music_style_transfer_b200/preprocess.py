@@ -140,3 +140,28 @@ def load_midi(data_dir, song_id, ext='mixcraft', debug=False):
         print("length of pianoroll: ", pianoroll.shape)
         print("midi files picked up:", midi_file)
     return pianoroll, onoff
+
+
+def get_data(data_dir, dataset_outpath, data_type, debug=False, piano_scores=None, styles=None):
+    """preprocess.py:163-200 with the HDF5 file replaced by a shard directory ``{dataset_outpath}_{data_type}``
+    (dataset.ShardManager mirrors io_manager.h5pyManager).  ``piano_scores`` / ``styles`` default to ``hp``'s."""
+    from .dataset import ShardManager
+    data_manager = ShardManager(f"{dataset_outpath}_{data_type}")
+    for song_id in (hp.piano_scores[data_type] if piano_scores is None else piano_scores):
+        pianoroll, onoff = load_midi(data_dir, song_id, debug=debug)
+        num_chunks = get_num_song_chunks(pianoroll)
+        pianoroll_list, onoff_list = process_pianoroll_into_chunks(pianoroll, onoff, song_id, num_chunks, debug=debug)
+        data_manager.write_pianoroll(pianoroll_list, onoff_list)
+        for style in (hp.styles if styles is None else styles):
+            try:
+                audio = load_audio(data_dir, song_id, style, debug=debug)
+            except ValueError:
+                # not all styles exist for all midi...  (the reference uses a bare except here, preprocess.py:185-190)
+                print(f"Couldnt load audio for song={song_id}, style={style}, skipping...")
+                continue
+            spec_list = process_audio_into_chunks(audio, style, song_id, num_chunks, debug=debug)
+            data_manager.write_spectrum(spec_list, style)
+            if debug is True:
+                assert pianoroll_list.shape[0] == spec_list.shape[0]
+                assert pianoroll_list.shape == onoff_list.shape
+    return data_manager

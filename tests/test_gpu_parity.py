@@ -250,6 +250,31 @@ def test_load_audio_dropin(pkg, tmp_path):
         pkg.preprocess.load_audio(str(tmp_path), 2240, "upright")
 
 
+def test_get_data_end_to_end(pkg, tmp_path):
+    """preprocess.py:163-200 on one synthetic song: midi + two style wavs -> shard dataset -> training items."""
+    from ml_music_style_transfer_b200 import midi, synth
+    from ml_music_style_transfer_b200.dataset import ShardDataset
+    seconds = 13.0
+    p, v, s, e = synth.midi_piece(7, seconds=seconds)
+    midi.write_midi_notes(str(tmp_path / "1749_x_mixcraft.mid"), p, v, s, e)
+    audio = {st: clip(60 + i, int(44100 * (seconds + 1)), "noise") for i, st in enumerate(("cuba", "upright"))}
+    for st, x in audio.items():
+        oaudio.write_wav(str(tmp_path / f"1749_x_{st}.wav"), x, 44100, bits=32)
+    mgr = pkg.preprocess.get_data(str(tmp_path), str(tmp_path / "out"), "train", debug=True, piano_scores=[1749],
+                                  styles=["cuba", "gentleman", "upright"])  # 'gentleman' is missing -> skipped
+    assert sorted(mgr.keys()) == ["onoff", "pianoroll", "spec_cuba", "spec_upright"]
+    ds = ShardDataset(str(tmp_path / "out_train"))
+    rp, rv, rs, re_ = midi.read_midi_notes(str(tmp_path / "1749_x_mixcraft.mid"))
+    ref_r, ref_o = opp.midi_notes_to_pianoroll(rp, rv, rs, re_)
+    n = opp.get_num_song_chunks(ref_r)
+    assert len(ds) == n and n >= 2
+    ra, rb = opp.process_pianoroll_into_chunks(ref_r, ref_o, 1749, n)
+    X, Xc, y = ds[1]
+    assert np.array_equal(X.numpy(), np.concatenate((ra[1], rb[1]), axis=-1).T.astype(np.float32))
+    refs = [opp.process_audio_into_chunks(audio[st], st, 1749, n)[1] for st in audio]
+    assert min(rel_l2(y.numpy(), r.astype(np.float64)) for r in refs) <= TOL
+
+
 # ---- P4: Griffin-Lim ------------------------------------------------------------------------
 def _sc(S, y, hop):
     return ogl.spectral_convergence(S, y, hop)

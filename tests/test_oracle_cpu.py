@@ -6,6 +6,7 @@ import re
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import audio as oaudio, griffinlim as ogl, mel as omel, pianoroll as opr, preprocess as opp, stft as ostft
 
@@ -235,6 +236,32 @@ def test_midi_reader_round_trip(tmp_path):
     order = np.lexsort((rp, rs))
     assert list(rp[order]) == [60, 64, 60, 72]
     assert np.allclose(np.sort(rs), np.sort(s)) and np.allclose(np.sort(re_), np.sort(e))
+
+
+def test_shard_dataset_container(tmp_path):
+    """dataset.ShardManager / ShardDataset mirror io_manager.h5pyManager / train.py::Dataseth5py."""
+    from ml_music_style_transfer_b200.dataset import ShardDataset, ShardManager
+    rng = np.random.default_rng(0)
+    m = ShardManager(str(tmp_path / "ds_train"))
+    rolls, oos, specs = [], [], {"cuba": [], "upright": []}
+    for n in (3, 2):  # two "songs" appended one after the other
+        r = (rng.random((n, 860, 128)) < 0.05).astype(np.float64)
+        o = np.sign(rng.standard_normal((n, 860, 128))).astype(np.float64) * (rng.random((n, 860, 128)) < 0.02)
+        m.write_pianoroll(r, o)
+        rolls.append(r); oos.append(o)
+        for st in specs:
+            sp = rng.random((n, 1025, 860)).astype(np.float32)
+            m.write_spectrum(sp, st)
+            specs[st].append(sp)
+    ds = ShardDataset(str(tmp_path / "ds_train"))
+    assert len(ds) == 5 and sorted(ds.styles) == ["spec_cuba", "spec_upright"]
+    X, Xc, y = ds[4]
+    assert X.shape == (256, 860) and Xc.shape == (1025, 860) and y.shape == (1025, 860) and X.dtype == torch.float32
+    R, O = np.concatenate(rolls), np.concatenate(oos)
+    assert np.array_equal(X.numpy(), np.concatenate((R[4], O[4]), axis=-1).T.astype(np.float32))
+    assert any(np.array_equal(y.numpy(), np.concatenate(specs[st])[4]) for st in specs)
+    with pytest.raises(ValueError):
+        m.write_spectrum(np.zeros((1, 1025, 100), dtype=np.float32), "cuba")
 
 
 def test_shard_ranges_partition():
