@@ -126,6 +126,16 @@ int mst_pianoroll_rasterize(const int32_t* d_pitch, const int32_t* d_velocity, c
                             const double* d_end, const int64_t* d_note_offsets, int n_pieces,
                             const int64_t* d_row_offsets, int64_t total_rows, int64_t total_notes, int fs,
                             uint8_t* d_roll, int8_t* d_onoff, int32_t* d_velsum, mst_stream_t stream);
+/* Same, followed by pretty_midi >= 0.2.9's CC64 sustain rule (get_piano_roll(pedal_threshold=64)): inside each
+ * pedal-down span [d_span_start, d_span_end) (columns of piece d_span_piece) every pitch keeps the running maximum of
+ * its velocity sum, then roll / onoff are derived from the sustained sums.  Spans are computed by the host from the
+ * CC64 events (int(cc.time * fs) on the host is already exact).  d_velsum is required when n_spans > 0. */
+int mst_pianoroll_rasterize_sustain(const int32_t* d_pitch, const int32_t* d_velocity, const double* d_start,
+                                    const double* d_end, const int64_t* d_note_offsets, int n_pieces,
+                                    const int64_t* d_row_offsets, int64_t total_rows, int64_t total_notes, int fs,
+                                    const int32_t* d_span_piece, const int64_t* d_span_start, const int64_t* d_span_end,
+                                    int n_spans, uint8_t* d_roll, int8_t* d_onoff, int32_t* d_velsum,
+                                    mst_stream_t stream);
 /* preprocess.py:80-96: out[c][j][p] = plane[c*stride_rows + j][p], j < chunk_rows; rows beyond
  * n_rows read as 0.  in: int8/uint8 plane; out_dtype MST_DTYPE_{I8,F32,F64} (reference: float64). */
 int mst_pianoroll_chunks(const void* d_plane, int64_t n_rows, int num_chunks, int chunk_rows, int stride_rows,

@@ -63,6 +63,35 @@ __global__ void rasterize_kernel(const int32_t* __restrict__ pitch, const int32_
   }
 }
 
+// CC64 sustain (pretty_midi >= 0.2.9 get_piano_roll, pedal_threshold=64): inside every pedal-down span [a, b) each
+// pitch keeps the running maximum of its velocity sum ("np.maximum.accumulate(subpr, axis=1)").  One thread per
+// (span, pitch); consecutive threads touch consecutive pitches, so every column step is one coalesced 512-byte row.
+__global__ void sustain_kernel(int32_t* __restrict__ velsum, const int64_t* __restrict__ row_off,
+                               const int32_t* __restrict__ span_piece, const int64_t* __restrict__ span_start,
+                               const int64_t* __restrict__ span_end, int n_spans) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int span = (int)(gid >> 7), p = (int)(gid & 127);
+  if (span >= n_spans) return;
+  const int piece = span_piece[span];
+  const int64_t r0 = row_off[piece], T = row_off[piece + 1] - r0;
+  int64_t a = span_start[span], b = span_end[span];
+  if (a < 0) a = 0;
+  if (b > T) b = T;  // NumPy slice clipping
+  int32_t run = 0;
+  for (int64_t c = a; c < b; ++c) {
+    int32_t* cell = velsum + (r0 + c) * 128 + p;
+    const int32_t v = *cell;
+    run = c == a ? v : max(run, v);
+    *cell = run;
+  }
+}
+
+// roll = (velsum != 0)  (preprocess.py:148)
+__global__ void binarize_kernel(const int32_t* __restrict__ velsum, int64_t n, uint8_t* __restrict__ roll) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    roll[i] = velsum[i] != 0 ? 1 : 0;
+}
+
 // onoff[i] = roll[i] - roll[i-1] with a zero row before the first row of each piece (preprocess.py:149-155).
 __global__ void onoff_kernel(const uint8_t* __restrict__ roll, const int64_t* __restrict__ row_off, int n_pieces,
                              int8_t* __restrict__ onoff) {
@@ -238,6 +267,32 @@ int mst_pianoroll_count_rows(const double* d_end, const int64_t* d_note_offsets,
                       reinterpret_cast<cudaStream_t>(stream)>>>(d_end, d_note_offsets, n_pieces, fs, d_rows_out);
   MST_CUDA_OK(cudaGetLastError());
   count_launch();
+  return MST_OK;
+}
+
+int mst_pianoroll_rasterize_sustain(const int32_t* d_pitch, const int32_t* d_velocity, const double* d_start,
+                                    const double* d_end, const int64_t* d_note_offsets, int n_pieces,
+                                    const int64_t* d_row_offsets, int64_t total_rows, int64_t total_notes, int fs,
+                                    const int32_t* d_span_piece, const int64_t* d_span_start, const int64_t* d_span_end,
+                                    int n_spans, uint8_t* d_roll, int8_t* d_onoff, int32_t* d_velsum,
+                                    mst_stream_t stream) {
+  if (n_spans < 0 || (n_spans > 0 && (!d_span_piece || !d_span_start || !d_span_end || !d_velsum)))
+    return fail(MST_ERR_INVALID, "sustain spans need span arrays and a velocity-sum buffer");
+  int rc = mst_pianoroll_rasterize(d_pitch, d_velocity, d_start, d_end, d_note_offsets, n_pieces, d_row_offsets, total_rows,
+                                   total_notes, fs, d_roll, d_onoff, d_velsum, stream);
+  if (rc || n_spans == 0 || total_rows == 0) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t threads = (int64_t)n_spans * 128;
+  sustain_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(d_velsum, d_row_offsets, d_span_piece, d_span_start,
+                                                                  d_span_end, n_spans);
+  MST_CUDA_OK(cudaGetLastError());
+  const int64_t n = total_rows * 128;
+  binarize_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, s>>>(d_velsum, n, d_roll);
+  MST_CUDA_OK(cudaGetLastError());
+  dim3 grid(64, (unsigned)std::min(n_pieces, 65535));
+  onoff_kernel<<<grid, 256, 0, s>>>(d_roll, d_row_offsets, n_pieces, d_onoff);
+  MST_CUDA_OK(cudaGetLastError());
+  count_launch(3);
   return MST_OK;
 }
 

@@ -108,7 +108,10 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> pianoroll_rasterize(const at::Ten
                                                                    const at::Tensor& start, const at::Tensor& end,
                                                                    const at::Tensor& note_offsets,
                                                                    const at::Tensor& row_offsets, int64_t total_rows,
-                                                                   int64_t fs, bool want_velsum) {
+                                                                   int64_t fs, bool want_velsum,
+                                                                   const c10::optional<at::Tensor>& span_piece,
+                                                                   const c10::optional<at::Tensor>& span_start,
+                                                                   const c10::optional<at::Tensor>& span_end) {
   want(pitch, at::kInt, "pitch"); want(velocity, at::kInt, "velocity");
   want(start, at::kDouble, "start"); want(end, at::kDouble, "end");
   want(note_offsets, at::kLong, "note_offsets"); want(row_offsets, at::kLong, "row_offsets");
@@ -117,13 +120,24 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> pianoroll_rasterize(const at::Ten
   TORCH_CHECK(row_offsets.numel() == n_pieces + 1, "row_offsets must have n_pieces + 1 entries");
   at::Tensor roll = at::empty({total_rows, 128}, pitch.options().dtype(at::kByte));
   at::Tensor onoff = at::empty({total_rows, 128}, pitch.options().dtype(at::kChar));
+  const int64_t n_spans = span_piece.has_value() ? span_piece->numel() : 0;
+  if (n_spans > 0) {
+    TORCH_CHECK(span_start.has_value() && span_end.has_value(), "span_start / span_end missing");
+    want(*span_piece, at::kInt, "span_piece"); want(*span_start, at::kLong, "span_start"); want(*span_end, at::kLong, "span_end");
+    TORCH_CHECK(span_start->numel() == n_spans && span_end->numel() == n_spans, "span arrays differ in length");
+    want_velsum = true;
+  }
   at::Tensor velsum = want_velsum ? at::empty({total_rows, 128}, pitch.options().dtype(at::kInt))
                                   : at::empty({0}, pitch.options().dtype(at::kInt));
-  check(mst_pianoroll_rasterize(pitch.data_ptr<int32_t>(), velocity.data_ptr<int32_t>(), start.data_ptr<double>(),
-                                end.data_ptr<double>(), note_offsets.data_ptr<int64_t>(), (int)n_pieces,
-                                row_offsets.data_ptr<int64_t>(), total_rows, pitch.numel(), (int)fs,
-                                roll.data_ptr<uint8_t>(), onoff.data_ptr<int8_t>(),
-                                want_velsum ? velsum.data_ptr<int32_t>() : nullptr, cur_stream()), "mst_pianoroll_rasterize");
+  check(mst_pianoroll_rasterize_sustain(pitch.data_ptr<int32_t>(), velocity.data_ptr<int32_t>(), start.data_ptr<double>(),
+                                        end.data_ptr<double>(), note_offsets.data_ptr<int64_t>(), (int)n_pieces,
+                                        row_offsets.data_ptr<int64_t>(), total_rows, pitch.numel(), (int)fs,
+                                        n_spans ? span_piece->data_ptr<int32_t>() : nullptr,
+                                        n_spans ? span_start->data_ptr<int64_t>() : nullptr,
+                                        n_spans ? span_end->data_ptr<int64_t>() : nullptr, (int)n_spans,
+                                        roll.data_ptr<uint8_t>(), onoff.data_ptr<int8_t>(),
+                                        want_velsum ? velsum.data_ptr<int32_t>() : nullptr, cur_stream()),
+        "mst_pianoroll_rasterize_sustain");
   return {roll, onoff, velsum};
 }
 
@@ -214,7 +228,8 @@ TORCH_LIBRARY(mst_b200, m) {
   m.def("stft_mel(Tensor audio, int batch, int plan, int n_mels, bool apply_log1p, int layout) -> Tensor");
   m.def("pianoroll_count_rows(Tensor end, Tensor note_offsets, int fs) -> Tensor");
   m.def("pianoroll_rasterize(Tensor pitch, Tensor velocity, Tensor start, Tensor end, Tensor note_offsets, "
-        "Tensor row_offsets, int total_rows, int fs, bool want_velsum) -> (Tensor, Tensor, Tensor)");
+        "Tensor row_offsets, int total_rows, int fs, bool want_velsum, Tensor? span_piece, Tensor? span_start, "
+        "Tensor? span_end) -> (Tensor, Tensor, Tensor)");
   m.def("pianoroll_chunks(Tensor plane, int num_chunks, int chunk_rows, int stride_rows, int out_dtype) -> Tensor");
   m.def("pianoroll_upsample(Tensor plane, Tensor row_offsets, Tensor sample_offsets, int total_samples, int fs, int sr, "
         "int pitch_lo, int n_keys, int out_dtype) -> Tensor");

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib, features
 from .preprocess import hyperparams, notes_to_pianoroll, process_spectrum_from_chunk
-from .midi import read_midi_notes
+from .midi import read_midi
 
 pp_hp = hyperparams()
 
@@ -31,8 +31,8 @@ class AudioSynthesizer():
 
     def process_custom_midi(self, midi_path):
         """inference.py:39-51: (pianoroll, onoff) transposed to (128, T)."""
-        pitch, velocity, start, end = read_midi_notes(midi_path)
-        pianoroll, onoff = notes_to_pianoroll(pitch, velocity, start, end, fs=self.wps)
+        pitch, velocity, start, end, cc64, end_time = read_midi(midi_path)
+        pianoroll, onoff = notes_to_pianoroll(pitch, velocity, start, end, fs=self.wps, cc64=cc64, end_time=end_time)
         return np.transpose(pianoroll, (1, 0)), np.transpose(onoff, (1, 0))
 
     def process_custom_audio(self, audio):

@@ -56,6 +56,10 @@ def _parse_track(data):
                 events.append((tick, 'on', a, v, ch))
             elif hi == 0x80 or hi == 0x90:
                 events.append((tick, 'off', a, v, ch))
+            elif hi == 0xB0:
+                events.append((tick, 'cc', a, v, ch))
+            elif hi == 0xE0:
+                events.append((tick, 'bend', a, v, ch))
         elif hi in (0xC0, 0xD0):
             pos += 1
         else:
@@ -65,6 +69,14 @@ def _parse_track(data):
 
 def read_midi_notes(path):
     """-> (pitch int32[], velocity int32[], start float64[], end float64[]) in file order of note-offs per track."""
+    return read_midi(path)[:4]
+
+
+def read_midi(path):
+    """-> (pitch, velocity, start, end, cc64 [(time, value), ...], end_time).
+
+    ``end_time`` is pretty_midi's get_end_time(): the latest note end, control change or pitch bend of any non-drum
+    channel; ``cc64`` are the sustain-pedal events in time order (all non-drum channels merged)."""
     with open(path, 'rb') as f:
         data = f.read()
     if data[:4] != b'MThd':
@@ -100,9 +112,20 @@ def read_midi_notes(path):
         return float(seg_time_a[i] + (tick - seg_tick_a[i]) * seg_scale_a[i])
 
     pitch, vel, start, end = [], [], [], []
+    cc64, other_times = [], []
     for tr in tracks:
         open_notes = {}
         for tick, kind, a, v, ch in tr:
+            if kind == 'cc':
+                if ch != 9:
+                    other_times.append(to_time(tick))
+                    if a == 64:
+                        cc64.append((tick, to_time(tick), v))
+                continue
+            if kind == 'bend':
+                if ch != 9:
+                    other_times.append(to_time(tick))
+                continue
             if kind == 'on':
                 open_notes.setdefault((ch, a), []).append((tick, v))
             elif kind == 'off':
@@ -119,17 +142,21 @@ def read_midi_notes(path):
                         open_notes[key] = keep
                     else:
                         del open_notes[key]
+    cc64.sort(key=lambda e: e[0])
+    end_time = max(list(end) + other_times) if (len(end) or other_times) else 0.0
     return (np.array(pitch, dtype=np.int32), np.array(vel, dtype=np.int32), np.array(start, dtype=np.float64),
-            np.array(end, dtype=np.float64))
+            np.array(end, dtype=np.float64), [(t, v) for _, t, v in cc64], float(end_time))
 
 
-def write_midi_notes(path, pitch, velocity, start, end, ticks_per_beat=480, bpm=120.0):
+def write_midi_notes(path, pitch, velocity, start, end, ticks_per_beat=480, bpm=120.0, cc64=None):
     """Tiny type-0 writer used by tests and synthetic corpora (times quantised to ticks)."""
     scale = ticks_per_beat * bpm / 60.0
     ev = []
     for p, v, s, e in zip(pitch, velocity, start, end):
         ev.append((int(round(s * scale)), 1, 0x90, int(p), int(v)))
         ev.append((int(round(e * scale)), 0, 0x80, int(p), 0))
+    for t, v in (cc64 or []):
+        ev.append((int(round(t * scale)), 2, 0xB0, 64, int(v)))
     ev.sort()
 
     def vlq(x):

@@ -17,7 +17,7 @@ class NoteBatch:
     pitch / velocity: int32; start / end: float64 seconds; note_offsets: int64 [n_pieces + 1].
     """
 
-    def __init__(self, pitch, velocity, start, end, note_offsets, device=None):
+    def __init__(self, pitch, velocity, start, end, note_offsets, device=None, end_times=None, pedals=None):
         device = _lib.require_cuda(device)
         self.device = device
         self.pitch = torch.as_tensor(np.asarray(pitch, dtype=np.int32)).to(device)
@@ -28,6 +28,10 @@ class NoteBatch:
         self.n_pieces = int(self.note_offsets.numel()) - 1
         if self.n_pieces < 1:
             raise ValueError("note_offsets needs at least two entries")
+        # optional per-piece extras of a parsed MIDI file: latest event time (pretty_midi get_end_time also counts
+        # control changes) and the CC64 event list [(time, value), ...] for the sustain rule
+        self.end_times = None if end_times is None else [float(t) for t in end_times]
+        self.pedals = pedals
 
     @classmethod
     def from_pieces(cls, pieces, device=None):
@@ -41,25 +45,54 @@ class NoteBatch:
         return cls(cat(ps, np.int32), cat(vs, np.int32), cat(ss, np.float64), cat(es, np.float64), offs, device)
 
 
-def rasterize(notes, fs, want_velsum=False):
+def pedal_spans(cc64_events, fs, pedal_threshold=64):
+    """pretty_midi's sustain state machine (get_piano_roll, pedal_threshold): [(time, value), ...] in file order ->
+    list of (start_col, end_col) pedal-down spans; a pedal still down at the end of the piece sustains nothing."""
+    spans, on, t_on = [], False, 0
+    for t, v in cc64_events:
+        now = int(float(t) * fs)
+        cur = v >= pedal_threshold
+        if not on and cur:
+            t_on, on = now, True
+        elif on and not cur:
+            spans.append((t_on, now))
+            on = False
+    return spans
+
+
+def rasterize(notes, fs, want_velsum=False, pedal_threshold=64):
     """-> (roll uint8 [sum T,128] in {0,1}, onoff int8 [sum T,128] in {-1,0,1}, row_offsets int64 [n_pieces+1], velsum|None).
 
-    T_p = int(fs * max note end) per piece (pretty_midi roll width); rows are time-major (the reference's ``.T``).
+    T_p = int(fs * end_time) per piece (pretty_midi roll width; end_time = latest note end, or ``notes.end_times``);
+    rows are time-major (the reference's ``.T``).  When ``notes.pedals`` holds CC64 events the sustain rule of
+    pretty_midi >= 0.2.9 (``pedal_threshold``, None = off) is applied before binarising.
     """
     o = _lib.ops()
-    rows = o.pianoroll_count_rows(notes.end, notes.note_offsets, int(fs))
+    if notes.end_times is None:
+        rows = o.pianoroll_count_rows(notes.end, notes.note_offsets, int(fs))
+    else:
+        rows = torch.tensor([int(fs * t) for t in notes.end_times], dtype=torch.int64, device=notes.device)
     row_offsets = torch.zeros(notes.n_pieces + 1, dtype=torch.int64, device=notes.device)
     torch.cumsum(rows, 0, out=row_offsets[1:])
     total_rows = int(row_offsets[-1].item())  # one small D2H: the roll has to be allocated
+    sp = ss = se = None
+    if notes.pedals is not None and pedal_threshold is not None:
+        spans = [(i, a, b) for i, ev in enumerate(notes.pedals) for a, b in pedal_spans(ev, fs, pedal_threshold) if b > a]
+        if spans:
+            sp = torch.tensor([x[0] for x in spans], dtype=torch.int32, device=notes.device)
+            ss = torch.tensor([x[1] for x in spans], dtype=torch.int64, device=notes.device)
+            se = torch.tensor([x[2] for x in spans], dtype=torch.int64, device=notes.device)
     roll, onoff, velsum = o.pianoroll_rasterize(notes.pitch, notes.velocity, notes.start, notes.end, notes.note_offsets,
-                                                row_offsets, total_rows, int(fs), bool(want_velsum))
-    return roll, onoff, row_offsets, (velsum if want_velsum else None)
+                                                row_offsets, total_rows, int(fs), bool(want_velsum), sp, ss, se)
+    return roll, onoff, row_offsets, (velsum if (want_velsum or sp is not None) else None)
 
 
-def get_piano_roll(pitch, velocity, start, end, fs=100):
-    """pretty_midi Instrument.get_piano_roll(fs) for one note list: float64 (128, T) velocity sums (NumPy)."""
-    nb = NoteBatch(pitch, velocity, start, end, [0, len(pitch)])
-    _, _, _, velsum = rasterize(nb, fs, want_velsum=True)
+def get_piano_roll(pitch, velocity, start, end, fs=100, cc64=None, end_time=None, pedal_threshold=64):
+    """pretty_midi Instrument.get_piano_roll(fs, pedal_threshold) for one note list (+ optional CC64 events):
+    float64 (128, T) velocity sums (NumPy)."""
+    nb = NoteBatch(pitch, velocity, start, end, [0, len(pitch)], end_times=None if end_time is None else [end_time],
+                   pedals=None if cc64 is None else [cc64])
+    _, _, _, velsum = rasterize(nb, fs, want_velsum=True, pedal_threshold=pedal_threshold)
     return velsum.t().to(torch.float64).cpu().numpy()
 
 

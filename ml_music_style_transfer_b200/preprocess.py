@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib, audio_io, features, pianoroll as _pr
-from .midi import read_midi_notes
+from .midi import read_midi, read_midi_notes
 
 
 class hyperparams(object):
@@ -118,10 +118,11 @@ def get_num_song_chunks(pianoroll, offset_percentage=0.1, max_chunks=100):
     return num_chunks
 
 
-def notes_to_pianoroll(pitch, velocity, start, end, fs=None, as_numpy=True):
-    """preprocess.py:147-155 for an explicit note list: (pianoroll, onoff), both (T,128)."""
-    nb = _pr.NoteBatch(pitch, velocity, start, end, [0, len(pitch)])
-    roll, onoff, _, _ = _pr.rasterize(nb, hp.wps if fs is None else fs)
+def notes_to_pianoroll(pitch, velocity, start, end, fs=None, as_numpy=True, cc64=None, end_time=None, pedal_threshold=64):
+    """preprocess.py:147-155 for an explicit note list (+ optional CC64 sustain events): (pianoroll, onoff), both (T,128)."""
+    nb = _pr.NoteBatch(pitch, velocity, start, end, [0, len(pitch)], end_times=None if end_time is None else [end_time],
+                       pedals=None if cc64 is None else [cc64])
+    roll, onoff, _, _ = _pr.rasterize(nb, hp.wps if fs is None else fs, pedal_threshold=pedal_threshold)
     if as_numpy:
         return roll.to(torch.float64).cpu().numpy(), onoff.to(torch.float64).cpu().numpy()
     return roll, onoff
@@ -134,8 +135,8 @@ def load_midi(data_dir, song_id, ext='mixcraft', debug=False):
         raise ValueError("couldnt find midi track!")
     elif len(midi_file) > 1:
         raise ValueError("multiple files picked up, issue:", midi_file)
-    pitch, velocity, start, end = read_midi_notes(midi_file[0])
-    pianoroll, onoff = notes_to_pianoroll(pitch, velocity, start, end)
+    pitch, velocity, start, end, cc64, end_time = read_midi(midi_file[0])
+    pianoroll, onoff = notes_to_pianoroll(pitch, velocity, start, end, cc64=cc64, end_time=end_time)
     if debug is True:
         print("length of pianoroll: ", pianoroll.shape)
         print("midi files picked up:", midi_file)

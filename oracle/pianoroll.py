@@ -19,8 +19,9 @@ __all__ = ["get_piano_roll", "binarize_and_onoff", "onoff_reference_loop", "upsa
            "process_pianoroll_into_chunks", "get_num_song_chunks"]
 
 
-def get_piano_roll(pitch, velocity, start, end, fs, end_time=None):
-    """(128, T) float64 velocity-sum roll.  ``start`` / ``end`` are float64 seconds."""
+def get_piano_roll(pitch, velocity, start, end, fs, end_time=None, cc64=None, pedal_threshold=64):
+    """(128, T) float64 velocity-sum roll.  ``start`` / ``end`` are float64 seconds.  ``cc64``: [(time, value), ...]
+    sustain-pedal events -> pretty_midi >= 0.2.9's running-maximum rule inside pedal-down spans."""
     pitch = np.asarray(pitch, dtype=np.int64)
     velocity = np.asarray(velocity, dtype=np.int64)
     start = np.asarray(start, dtype=np.float64)
@@ -32,6 +33,17 @@ def get_piano_roll(pitch, velocity, start, end, fs, end_time=None):
     roll = np.zeros((128, int(fs * end_time)))
     for p, v, s, e in zip(pitch, velocity, start, end):
         roll[int(p), int(float(s) * fs):int(float(e) * fs)] += int(v)
+    if cc64 is not None and pedal_threshold is not None:
+        time_pedal_on, is_pedal_on = 0, False
+        for t, val in cc64:
+            time_now = int(float(t) * fs)
+            is_current_pedal_on = val >= pedal_threshold
+            if not is_pedal_on and is_current_pedal_on:
+                time_pedal_on, is_pedal_on = time_now, True
+            elif is_pedal_on and not is_current_pedal_on:
+                subpr = roll[:, time_pedal_on:time_now]
+                roll[:, time_pedal_on:time_now] = np.maximum.accumulate(subpr, axis=1)
+                is_pedal_on = False
     return roll
 
 

@@ -45,7 +45,7 @@ def get_num_song_chunks(pianoroll, offset_percentage=0.1, max_chunks=100):
     return _pr.get_num_song_chunks(pianoroll.shape[0], offset_percentage, max_chunks, hp.spc * hp.wps, hp.stride)
 
 
-def midi_notes_to_pianoroll(pitch, velocity, start, end, fs=None):
+def midi_notes_to_pianoroll(pitch, velocity, start, end, fs=None, cc64=None, end_time=None):
     """preprocess.py:146-155 with the SMF parse replaced by explicit note arrays."""
-    roll = _pr.get_piano_roll(pitch, velocity, start, end, hp.wps if fs is None else fs)
+    roll = _pr.get_piano_roll(pitch, velocity, start, end, hp.wps if fs is None else fs, end_time=end_time, cc64=cc64)
     return _pr.binarize_and_onoff(roll)

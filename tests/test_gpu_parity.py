@@ -203,6 +203,39 @@ def test_pianoroll_batch_bit_exact(pkg, gpu, fs, sr, pitch_lo, n_keys):
         assert np.array_equal(blk, opr.upsample_to_audio_rate(ref_o, fs, sr, N, pitch_lo, n_keys, np.float32))
 
 
+def test_pianoroll_sustain_pedal(pkg, gpu, tmp_path):
+    """CC64 sustain: device running-max over pedal spans == pretty_midi rule (oracle), bit exact, batch + file."""
+    from ml_music_style_transfer_b200 import midi, synth
+    P = pkg.pianoroll
+    rng = np.random.default_rng(4)
+    pieces, pedals, ends = [], [], []
+    for i in range(4):
+        p, v, s, e = synth.midi_piece(20 + i, seconds=6.0)
+        times = np.sort(rng.uniform(0, 6.5, 14))
+        cc = [(float(t), int(rng.choice([0, 20, 64, 100, 127]))) for t in times]
+        pieces.append((p, v, s, e)); pedals.append(cc); ends.append(max(float(e.max()), cc[-1][0]))
+    pedals[3] = []  # a piece without pedal events
+    nb = P.NoteBatch.from_pieces(pieces, device=gpu)
+    nb.pedals, nb.end_times = pedals, ends
+    roll, onoff, row_off, velsum = P.rasterize(nb, 172)
+    ro = row_off.cpu().numpy()
+    for i, (p, v, s, e) in enumerate(pieces):
+        ref_v = opr.get_piano_roll(p, v, s, e, 172, end_time=ends[i], cc64=pedals[i])
+        ref_r, ref_o = opr.binarize_and_onoff(ref_v)
+        assert ro[i + 1] - ro[i] == ref_v.shape[1]
+        assert np.array_equal(velsum[ro[i]:ro[i + 1]].cpu().numpy().T, ref_v)
+        assert np.array_equal(roll[ro[i]:ro[i + 1]].cpu().numpy(), ref_r)
+        assert np.array_equal(onoff[ro[i]:ro[i + 1]].cpu().numpy(), ref_o)
+    # through a MIDI file and the load_midi drop-in
+    p, v, s, e = pieces[0]
+    midi.write_midi_notes(str(tmp_path / "2308_y_mixcraft.mid"), p, v, s, e, cc64=pedals[0])
+    got_r, got_o = pkg.preprocess.load_midi(str(tmp_path), 2308)
+    rp, rv, rs, re_, cc, end_time = midi.read_midi(str(tmp_path / "2308_y_mixcraft.mid"))
+    ref_r, ref_o = opp.midi_notes_to_pianoroll(rp, rv, rs, re_, cc64=cc, end_time=end_time)
+    assert np.array_equal(got_r, ref_r) and np.array_equal(got_o, ref_o)
+    assert got_r.sum() > opp.midi_notes_to_pianoroll(rp, rv, rs, re_)[0].sum()  # the pedal really sustained something
+
+
 def test_process_pianoroll_into_chunks_dropin(pkg):
     from ml_music_style_transfer_b200 import synth
     p, v, s, e = synth.midi_piece(3, seconds=14.0)

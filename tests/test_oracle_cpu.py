@@ -114,6 +114,30 @@ def test_pianoroll_known_answer():
     assert np.array_equal(oo, opr.onoff_reference_loop(pr))
 
 
+def test_pianoroll_sustain_pedal_known_answer():
+    """pretty_midi >= 0.2.9: inside a pedal-down span every pitch keeps the running max of its velocity sum."""
+    fs = 100
+    cc = [(0.2, 127), (1.5, 0), (1.8, 64), (1.9, 63), (2.5, 100)]  # last press is never released -> no effect
+    roll = opr.get_piano_roll([60, 64, 67], [100, 50, 30], [0.0, 1.0, 2.6], [0.5, 1.2, 3.0], fs, cc64=cc)
+    assert roll.shape == (128, 300)
+    assert (roll[60, 0:150] == 100).all() and (roll[60, 150:] == 0).all()     # held from 0.5 until the release at 1.5
+    assert (roll[64, 100:150] == 50).all() and roll[64, 99] == 0 and roll[64, 150] == 0
+    assert (roll[67, 260:300] == 30).all() and roll[67, 259] == 0             # pedal still down at the end: untouched
+    plain = opr.get_piano_roll([60, 64, 67], [100, 50, 30], [0.0, 1.0, 2.6], [0.5, 1.2, 3.0], fs)
+    assert (plain[60, 50:] == 0).all()
+    from ml_music_style_transfer_b200.pianoroll import pedal_spans
+    assert pedal_spans(cc, fs) == [(20, 150), (180, 190)]
+
+
+def test_midi_reader_control_changes(tmp_path):
+    from ml_music_style_transfer_b200 import midi
+    path = str(tmp_path / "p.mid")
+    midi.write_midi_notes(path, [60], [90], [0.0], [0.5], cc64=[(0.25, 127), (2.0, 0)])
+    p, v, s, e, cc, end_time = midi.read_midi(path)
+    assert list(p) == [60] and [val for _, val in cc] == [127, 0]
+    assert abs(cc[0][0] - 0.25) < 1e-9 and abs(end_time - 2.0) < 1e-9  # the late pedal release extends the roll
+
+
 def test_onoff_loop_equals_difference_random():
     from ml_music_style_transfer_b200 import synth
     p, v, s, e = synth.midi_piece(0, seconds=6.0)
