@@ -315,36 +315,63 @@ def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrie
     n_notes = int(no[n])
     h_notes = [torch.from_numpy(np.ascontiguousarray(a[:n_notes])).pin_memory() for a in notes_h[:4]]
     h_noff = torch.from_numpy(np.ascontiguousarray(no[:n + 1])).pin_memory()
-    batch = F.ClipBatch.uniform(n, CLIP_LEN, HOP, device=device)
-    gl_batch = F.ClipBatch.from_frames([T_FRAMES] * n, HOP, device=device)
+    # The batch is cut into chunks that alternate between two CUDA streams, so that the H2D copies of chunk i+1 and the
+    # D2H copies of chunk i-1 overlap the kernels of chunk i (the library launches on torch's current stream).
+    n_chunks = max(1, min(args.e2e_chunks, n // 256)) if n >= 512 else 1
+    bounds = [(n * i) // n_chunks for i in range(n_chunks + 1)]
+    chunks = []
+    rows_per_clip = int(ROLL_FS * CLIP_SECONDS)
+    for ci in range(n_chunks):
+        a0, a1 = bounds[ci], bounds[ci + 1]
+        m = a1 - a0
+        n0, n1 = int(no[a0]), int(no[a1])
+        chunks.append(dict(
+            a0=a0, a1=a1, m=m,
+            batch=F.ClipBatch.uniform(m, CLIP_LEN, HOP, device=device),
+            gl_batch=F.ClipBatch.from_frames([T_FRAMES] * m, HOP, device=device),
+            notes=[t[n0:n1] for t in h_notes],
+            noff=torch.from_numpy(np.ascontiguousarray(no[a0:a1 + 1] - no[a0])).pin_memory()))
+    streams = [torch.cuda.Stream(device=device) for _ in range(2)]
     d2h_roll = [0]
 
     def step():
-        a = h_audio.to(device, non_blocking=True)
-        mel = F.melspectrogram_batch(a, batch, plan, log1p=True, layout=F.BIN_MAJOR)
-        h_mel.copy_(mel, non_blocking=True)
-        nb = PR.NoteBatch.__new__(PR.NoteBatch)
-        nb.device = device
-        nb.pitch, nb.velocity, nb.start, nb.end = [t.to(device, non_blocking=True) for t in h_notes]
-        nb.note_offsets = h_noff.to(device, non_blocking=True)
-        nb.n_pieces = n
-        roll, onoff, row_off, _ = PR.rasterize(nb, ROLL_FS)
-        rows = min(roll.shape[0], roll_rows)
-        h_roll[:rows].copy_(roll[:rows], non_blocking=True)
-        h_onoff[:rows].copy_(onoff[:rows], non_blocking=True)
-        d2h_roll[0] = 2 * rows * 128
-        for s in range(0, n, sub):
-            e = min(n, s + sub)
-            ro = row_off[s:e + 1]
-            ua, _ = PR.upsample(roll, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
-            ub, _ = PR.upsample(onoff, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
-            if planes_to_host:
-                m = (e - s) * N_KEYS * CLIP_LEN
-                h_planes[:m].copy_(ua, non_blocking=True)
-                h_planes[m:2 * m].copy_(ub, non_blocking=True)
-        Sd = h_S.to(device, non_blocking=True)
-        y = F.griffinlim_batch(Sd, gl_batch, n_iter=GL_ITERS, momentum=0.99, init="random", seed=7, layout=F.FRAME_MAJOR)
-        h_y.copy_(y, non_blocking=True)
+        d2h_roll[0] = 0
+        main = torch.cuda.current_stream()
+        for s_ in streams:
+            s_.wait_stream(main)
+        for ci, ch in enumerate(chunks):
+            a0, a1, m = ch["a0"], ch["a1"], ch["m"]
+            with torch.cuda.stream(streams[ci % 2]):
+                a = h_audio[a0 * CLIP_LEN:a1 * CLIP_LEN].to(device, non_blocking=True)
+                mel = F.melspectrogram_batch(a, ch["batch"], plan, log1p=True, layout=F.BIN_MAJOR)
+                h_mel[a0 * N_MELS * T_FRAMES:a1 * N_MELS * T_FRAMES].copy_(mel, non_blocking=True)
+                nb = PR.NoteBatch.__new__(PR.NoteBatch)
+                nb.device = device
+                nb.pitch, nb.velocity, nb.start, nb.end = [t.to(device, non_blocking=True) for t in ch["notes"]]
+                nb.note_offsets = ch["noff"].to(device, non_blocking=True)
+                nb.n_pieces, nb.end_times, nb.pedals = m, None, None
+                roll, onoff, row_off, _ = PR.rasterize(nb, ROLL_FS)
+                rows = min(roll.shape[0], m * rows_per_clip)
+                r0 = a0 * rows_per_clip
+                h_roll[r0:r0 + rows].copy_(roll[:rows], non_blocking=True)
+                h_onoff[r0:r0 + rows].copy_(onoff[:rows], non_blocking=True)
+                d2h_roll[0] += 2 * rows * 128
+                for s in range(0, m, sub):
+                    e = min(m, s + sub)
+                    ro = row_off[s:e + 1]
+                    ua, _ = PR.upsample(roll, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
+                    ub, _ = PR.upsample(onoff, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
+                    if planes_to_host:
+                        k = (e - s) * N_KEYS * CLIP_LEN
+                        h_planes[:k].copy_(ua, non_blocking=True)
+                        h_planes[k:2 * k].copy_(ub, non_blocking=True)
+                Sd = h_S[a0 * T_FRAMES * K:a1 * T_FRAMES * K].to(device, non_blocking=True)
+                y = F.griffinlim_batch(Sd, ch["gl_batch"], n_iter=GL_ITERS, momentum=0.99, init="random", seed=7,
+                                       layout=F.FRAME_MAJOR)
+                L = HOP * (T_FRAMES - 1)
+                h_y[a0 * L:a1 * L].copy_(y, non_blocking=True)
+        for s_ in streams:
+            main.wait_stream(s_)
         torch.cuda.synchronize()
 
     step()
@@ -365,7 +392,7 @@ def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrie
     h2d = h_audio.numel() * 4 + h_S.numel() * 4 + sum(t.numel() * t.element_size() for t in h_notes) + h_noff.numel() * 8
     d2h = h_mel.numel() * 4 + h_y.numel() * 4 + d2h_roll[0] + (2 * n * N_KEYS * CLIP_LEN if planes_to_host else 0)
     return {"value": world * n * CLIP_SECONDS / (ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "clips_per_gpu": n, "ms_per_step": ms,
+            "d2h_bytes_per_step": int(d2h), "clips_per_gpu": n, "ms_per_step": ms, "pipeline_chunks": n_chunks,
             "outputs_to_host": "log-mel, waveforms, frame-rate roll+onoff" + (", audio-rate planes" if planes_to_host else
                                " (audio-rate planes stay on the device for the model)")}
 
@@ -444,6 +471,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=16384, help="clips per GPU (C4: 16384)")
     ap.add_argument("--e2e-clips", type=int, default=4096, help="clips per GPU for the host-buffer end-to-end pass")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline depth of the end-to-end pass (chunks over 2 streams)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
