@@ -68,6 +68,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+// 1-D bulk asynchronous copy global -> shared (TMA engine, no tensor map), completion on an mbarrier.
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -123,7 +130,7 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 struct GemmParams {
   MelSlices slices;              // banded filterbank geometry
-  const __nv_bfloat16* w_hi;     // [sum N_s][64] banded filterbank, high part
+  const __nv_bfloat16* w_hi;     // [sum N_s][64] banded filterbank, high part, ALREADY in the swizzled shared-memory image
   const __nv_bfloat16* w_lo;     // same, low part
   int w_rows;                    // sum N_s
   int n_mels, n_cols;            // mel rows, TMEM columns per accumulator (n_mels rounded up to 32)
@@ -150,26 +157,25 @@ mel_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
   uint64_t* empty = bars + kStages;           // [kStages] MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;   // [2] MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;       // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* wbar = tmem_empty + 2;            // [1] filterbank image landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (P.n_rows + kTileFrames - 1) / kTileFrames;
   const uint32_t tmem_cols = 2 * P.n_cols;  // 256 or 512: power of two >= 32
 
   // ---- one-time setup -------------------------------------------------------------------------------------------
-  // banded filterbank -> shared memory in the UMMA K-major SWIZZLE_128B layout (16-byte chunk c of row r at c ^ (r & 7))
-  for (int i = threadIdx.x; i < P.w_rows * 8; i += blockDim.x) {
-    const int r = i >> 3, c = i & 7;
-    const uint4 vh = __ldg(reinterpret_cast<const uint4*>(P.w_hi) + i);
-    const uint4 vl = __ldg(reinterpret_cast<const uint4*>(P.w_lo) + i);
-    const int dst = r * 128 + ((c ^ (r & 7)) << 4);
-    *reinterpret_cast<uint4*>(s_whi + dst) = vh;
-    *reinterpret_cast<uint4*>(s_wlo + dst) = vl;
-  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+    mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // banded filterbank: the plan stores it as the exact shared-memory image (UMMA K-major SWIZZLE_128B: 16-byte
+    // chunk c of row r at c ^ (r & 7)), so two bulk copies bring in all ~92 KB without touching registers
+    const uint32_t wbytes = (uint32_t)P.w_rows * 128;
+    mbar_arrive_expect_tx(wbar, 2 * wbytes);
+    bulk_load(s_whi, P.w_hi, wbytes, wbar);
+    bulk_load(s_wlo, P.w_lo, wbytes, wbar);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -205,6 +211,7 @@ mel_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     // ===== MMA issuer (one thread) ===============================================================================
     if (lane == 0) {
       uint32_t it = 0, local_tile = 0;
+      mbar_wait(wbar, 0);  // filterbank image resident
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local_tile) {
         const int buf = local_tile & 1;
         mbar_wait(tmem_empty + buf, (local_tile >> 1) & 1);  // accumulator drained and re-zeroed by the epilogue

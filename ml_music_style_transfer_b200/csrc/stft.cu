@@ -275,6 +275,19 @@ int mst_mel_plan_create(const float* W, int n_mels, int n_bins, mst_mel_plan_t**
       }
   }
   p->w_rows = (int)(hi.size() / 64);
+  {
+    // store the exact shared-memory image the projection kernel wants: K-major SWIZZLE_128B, i.e. the 16-byte
+    // chunk c (8 bf16) of 128-byte row r lives at chunk position c ^ (r & 7)
+    std::vector<__nv_bfloat16> ih(hi.size()), il(lo.size());
+    for (int r = 0; r < p->w_rows; ++r)
+      for (int c = 0; c < 8; ++c)
+        for (int e = 0; e < 8; ++e) {
+          ih[(size_t)r * 64 + ((c ^ (r & 7)) * 8) + e] = hi[(size_t)r * 64 + c * 8 + e];
+          il[(size_t)r * 64 + ((c ^ (r & 7)) * 8) + e] = lo[(size_t)r * 64 + c * 8 + e];
+        }
+    hi.swap(ih);
+    lo.swap(il);
+  }
   const size_t band_bytes = std::max<size_t>(1, hi.size()) * sizeof(__nv_bfloat16);
   if (cudaMalloc(&p->d_dense, sizeof(float) * (size_t)n_mels * n_bins) != cudaSuccess ||
       cudaMalloc(&p->d_band_hi, band_bytes) != cudaSuccess || cudaMalloc(&p->d_band_lo, band_bytes) != cudaSuccess ||
