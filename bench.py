@@ -153,10 +153,12 @@ def run_ours(args):
     audio_seconds = n_clips * CLIP_SECONDS
     audio = make_audio_device(n_clips, device, seed0=1000 * rank)
     batch = F.ClipBatch.uniform(n_clips, CLIP_LEN, HOP, device=device)
-    gl_batch = F.ClipBatch.from_frames([T_FRAMES] * n_clips, HOP, device=device)
+    gl_sub = min(n_clips, args.gl_sub)        # clips per Griffin-Lim call (bounds the HBM workspace: 20 B/bin + accumulators)
+    gl_batches = [(s0, min(n_clips, s0 + gl_sub)) for s0 in range(0, n_clips, gl_sub)]
+    gl_batches = [(a0, a1, F.ClipBatch.from_frames([T_FRAMES] * (a1 - a0), HOP, device=device)) for a0, a1 in gl_batches]
     plan = F.MelPlan.get(SR, N_FFT, N_MELS, device=device)
     notes_h = make_notes(n_clips, seed0=99 + 1000 * rank)
-    roll_sub = min(n_clips, 1024)             # pieces per piano-roll launch (ring of output buffers)
+    roll_sub = max(1, min(n_clips, int(1024 * 4.0 / CLIP_SECONDS)))   # pieces per piano-roll launch (ring of output buffers)
     notes = PR.NoteBatch(*notes_h, device=device)
     # GL input: the magnitude spectrogram the model would emit (made once, untimed)
     S = F.stft_batch(audio, batch, "magnitude", F.FRAME_MAJOR)
@@ -177,8 +179,11 @@ def run_ours(args):
         return outs
 
     def stage_c(n_iter=GL_ITERS):
-        return F.griffinlim_batch(S, gl_batch, n_iter=n_iter, momentum=0.99, init_phase=None, init="random", seed=7,
-                                  layout=F.FRAME_MAJOR)
+        y = None
+        for a0, a1, gb in gl_batches:
+            y = F.griffinlim_batch(S[a0 * T_FRAMES * K:a1 * T_FRAMES * K], gb, n_iter=n_iter, momentum=0.99,
+                                   init_phase=None, init="random", seed=7, layout=F.FRAME_MAJOR)
+        return y
 
     def barrier():
         if world > 1:
@@ -223,6 +228,7 @@ def run_ours(args):
     del fill_buf
 
     # kernel-level roofline of the dominant kernel (Griffin-Lim iteration): (t[32 iters] - t[0 iters]) / 32
+    med = lambda x: float(np.median(x))
     t0 = float(np.median(timed(lambda: stage_c(0), 3)))
     t32 = float(np.median(tc))
     iter_ms = (t32 - t0) / GL_ITERS
@@ -231,8 +237,6 @@ def run_ours(args):
     gl_total_bytes = n_clips * (GL_ITERS * (36 * K * T_FRAMES + 8 * L) + 12 * K * T_FRAMES + 4 * L)
     a_bytes = n_clips * (4 * CLIP_LEN + 4 * N_MELS * T_FRAMES)
     b_bytes = n_clips * 2 * N_KEYS * CLIP_LEN
-    med = lambda x: float(np.median(x))
-
     # max over ranks
     if world > 1:
         t = torch.tensor([total_ms, med(ta), med(tb), med(tc), iter_ms], device=device, dtype=torch.float64)
@@ -241,7 +245,28 @@ def run_ours(args):
     else:
         ma, mb, mc = med(ta), med(tb), med(tc)
     ms_per_step = total_ms / args.steps
-    value = world * audio_seconds / (ms_per_step * 1e-3)
+    total_audio = world * audio_seconds
+    if world > 1:
+        ta_ = torch.tensor([audio_seconds], device=device, dtype=torch.float64)
+        dist.all_reduce(ta_, op=dist.ReduceOp.SUM)
+        total_audio = float(ta_.item())
+    value = total_audio / (ms_per_step * 1e-3)
+
+    # ---- configs[0]/[1] of BASELINE.json: ONE 30 s clip (latency view; tiny against a B200, reported for completeness) ----
+    single = None
+    if rank == 0 and not args.no_single:
+        n30 = 30 * SR
+        a30 = make_audio_device(max(1, -(-n30 // CLIP_LEN)), device, 77)[:n30].contiguous()
+        b30 = F.ClipBatch.uniform(1, n30, HOP, device=device)
+        b30r = F.ClipBatch.uniform(1, n30, 256, device=device)   # the repo's own hop (preprocess.py:40)
+        T30 = b30.total_frames
+        g30 = F.ClipBatch.from_frames([T30], HOP, device=device)
+        S30 = F.stft_batch(a30, b30, "magnitude", F.FRAME_MAJOR)
+        t_lm = med(timed(lambda: F.melspectrogram_batch(a30, b30, plan, log1p=True, layout=F.BIN_MAJOR), 20))
+        t_lp = med(timed(lambda: F.stft_batch(a30, b30r, "log1p_power", F.FRAME_MAJOR), 20))
+        t_gl = med(timed(lambda: F.griffinlim_batch(S30, g30, n_iter=GL_ITERS, seed=3, layout=F.FRAME_MAJOR), 10))
+        single = {"logmel_hop512_ms": t_lm, "log1p_power_hop256_ms": t_lp, "griffinlim32_hop512_ms": t_gl,
+                  "griffinlim32_audio_s_per_s": 30.0 / (t_gl * 1e-3), "frames": T30}
 
     # ---- e2e: NumPy-facing API with pinned host buffers ------------------------------------------------------------
     e2e = None
@@ -251,12 +276,12 @@ def run_ours(args):
 
     if rank == 0:
         stages = {
-            "stft_logmel": {"ms": ma, "audio_s_per_s": world * audio_seconds / (ma * 1e-3),
+            "stft_logmel": {"ms": ma, "audio_s_per_s": total_audio / (ma * 1e-3),
                             "hbm_frac": a_bytes / (ma * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": a_bytes},
-            "pianoroll_upsample": {"ms": mb, "audio_s_per_s": world * audio_seconds / (mb * 1e-3),
+            "pianoroll_upsample": {"ms": mb, "audio_s_per_s": total_audio / (mb * 1e-3),
                                    "hbm_frac": b_bytes / (mb * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": b_bytes,
                                    "write_only_peak_gbs": write_peak, "write_only_frac": b_bytes / (mb * 1e-3) / 1e9 / write_peak},
-            "griffinlim32": {"ms": mc, "audio_s_per_s": world * audio_seconds / (mc * 1e-3),
+            "griffinlim32": {"ms": mc, "audio_s_per_s": total_audio / (mc * 1e-3),
                              "hbm_frac": gl_total_bytes / (mc * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": gl_total_bytes},
         }
         achieved = gl_iter_bytes / (iter_ms * 1e-3) / 1e9
@@ -267,11 +292,15 @@ def run_ours(args):
                 traffic = json.load(f)["gl_iteration_dram_bytes_per_clip"] * n_clips
         line = {
             "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "c5" else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C4: {n_clips} clips/GPU x 4 s @ 22.05 kHz, n_fft 2048, hop 512, 128 mels; "
-                                   f"88-key roll @ 250 Hz -> audio rate (int8, roll+onoff); Griffin-Lim {GL_ITERS} it",
-                       "clips_per_gpu": n_clips, "l2_policy": "inputs larger than L2 (5.8 GB audio, 11.6 GB spectrogram per GPU)",
+            "config": {"workload": f"{args.workload.upper()}: {n_clips} clips/GPU x {CLIP_SECONDS:g} s @ 22.05 kHz, n_fft 2048, "
+                                   f"hop 512, 128 mels; 88-key roll @ 250 Hz -> audio rate (int8, roll+onoff); "
+                                   f"Griffin-Lim {GL_ITERS} it",
+                       "clips_per_gpu": n_clips,
+                       "l2_policy": f"inputs larger than L2 ({n_clips * CLIP_LEN * 4 / 1e9:.1f} GB audio, "
+                                    f"{n_clips * T_FRAMES * K * 4 / 1e9:.1f} GB spectrogram per GPU)",
                        "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
             "stages": stages,
             "roofline": {"bound": "hbm", "kernel": "gl_kernel<false> (one Griffin-Lim iteration)", "achieved": achieved,
@@ -279,6 +308,8 @@ def run_ours(args):
                          "ms_per_launch": iter_ms, "algorithmic_bytes_per_launch": gl_iter_bytes, "traffic": traffic},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall_s,
         }
+        if not args.no_single:
+            line["single_clip_30s"] = single
         if e2e is not None:
             line["e2e"] = e2e
             line["e2e_planes_to_host"] = e2e_all
@@ -306,7 +337,7 @@ def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrie
     h_S.copy_(S_d[:n * T_FRAMES * K])
     h_mel = torch.empty(n * N_MELS * T_FRAMES, dtype=torch.float32).pin_memory()
     h_y = torch.empty(n * HOP * (T_FRAMES - 1), dtype=torch.float32).pin_memory()
-    sub = min(n, 256)
+    sub = max(1, min(n, int(256 * 4.0 / CLIP_SECONDS)))
     h_planes = torch.empty(2 * sub * N_KEYS * CLIP_LEN, dtype=torch.int8).pin_memory() if planes_to_host else None
     roll_rows = n * int(ROLL_FS * CLIP_SECONDS)
     h_roll = torch.empty((roll_rows, 128), dtype=torch.uint8).pin_memory()
@@ -469,7 +500,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips", type=int, default=16384, help="clips per GPU (C4: 16384)")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4: 16384 x 4 s clips per GPU (weak scaling); c5: MusicNet-piano-scale corpus, 4080 x 30 s clips "
+                         "in total, sharded over the ranks (strong scaling)")
+    ap.add_argument("--clips", type=int, default=None, help="clips per GPU (default: 16384 for c4, 4080/world for c5)")
+    ap.add_argument("--gl-sub", type=int, default=16384, help="clips per Griffin-Lim call (workspace bound)")
+    ap.add_argument("--no-single", action="store_true", help="skip the single 30 s clip latency section")
     ap.add_argument("--e2e-clips", type=int, default=4096, help="clips per GPU for the host-buffer end-to-end pass")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline depth of the end-to-end pass (chunks over 2 streams)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
@@ -477,6 +513,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per GL-iteration launch (from profiles/)")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "c5":
+        global CLIP_SECONDS, CLIP_LEN, T_FRAMES
+        CLIP_SECONDS, CLIP_LEN = 30.0, 30 * SR
+        T_FRAMES = 1 + CLIP_LEN // HOP
+        if args.clips is None:
+            rank = int(os.environ.get("RANK", "0"))
+            base, extra = divmod(4080, world)
+            args.clips = base + (1 if rank < extra else 0)
+        args.gl_sub = min(args.gl_sub, 1024)
+        args.e2e_clips = min(args.e2e_clips, 256)
+    elif args.clips is None:
+        args.clips = 16384
     if args.impl == "reference":
         run_reference(args)
     else:

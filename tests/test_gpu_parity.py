@@ -421,3 +421,54 @@ def test_griffinlim_batch_full_size_round_trip(pkg, gpu):
     # and a few iterations from there must keep the consistent spectrogram (fixed point of the projection)
     out2 = F.griffinlim_batch(S, gb, n_iter=3, init_phase=ph.float().contiguous(), layout=F.FRAME_MAJOR).cpu().numpy()
     assert np.abs(out2 - y)[2048:l - 2048].max() < 5e-3
+
+
+# ---- size-independent properties at benchmark scale (C4 shapes) ------------------------------------------------------
+def test_full_size_properties(pkg, gpu):
+    """2048 clips x 4 s (an eighth of C4 per GPU): properties that need no oracle run at that size."""
+    import bench
+    F, PR = pkg.features, pkg.pianoroll
+    n = 2048
+    audio = bench.make_audio_device(n, gpu, 5)
+    batch = F.ClipBatch.uniform(n, bench.CLIP_LEN, bench.HOP, device=gpu)
+    plan = F.MelPlan.get(bench.SR, device=gpu)
+    # (1) power-mel is quadratic in the signal: mel(2x) == 4 mel(x) (exact powers of two survive every rounding)
+    m1 = F.melspectrogram_batch(audio, batch, plan, log1p=False, layout=F.BIN_MAJOR)
+    m2 = F.melspectrogram_batch(audio * 2.0, batch, plan, log1p=False, layout=F.BIN_MAJOR)
+    assert torch.equal(m2, 4.0 * m1)
+    assert torch.isfinite(m1).all() and (m1 >= 0).all()
+    # (2) layouts agree: bin-major == transpose of frame-major, clip by clip
+    fm = F.melspectrogram_batch(audio, batch, plan, log1p=False, layout=F.FRAME_MAJOR).view(n, bench.T_FRAMES, 128)
+    assert torch.equal(m1.view(n, 128, bench.T_FRAMES), fm.transpose(1, 2))
+    # (3) Parseval per frame on the log-power path: sum_k c_k |X_k|^2 == N * sum (w x)^2 for interior frames
+    P = F.stft_batch(audio[:64 * bench.CLIP_LEN], F.ClipBatch.uniform(64, bench.CLIP_LEN, bench.HOP, device=gpu), "power",
+                     F.FRAME_MAJOR).view(64, bench.T_FRAMES, 1025).double()
+    wts = torch.full((1025,), 2.0, dtype=torch.float64, device=gpu)
+    wts[0] = wts[1024] = 1.0
+    lhs = (P * wts).sum(-1)[:, 10]
+    win = torch.hann_window(2048, periodic=True, dtype=torch.float64, device=gpu)
+    x = audio[:64 * bench.CLIP_LEN].view(64, -1)[:, 10 * 512 - 1024:10 * 512 + 1024].double()
+    rhs = 2048.0 * ((x * win) ** 2).sum(-1)
+    assert torch.allclose(lhs, rhs, rtol=1e-5)
+    # (4) piano roll at scale: every audio-rate row is the hold-replication of its frame-rate row, checked by an exact
+    # integer identity (sum over samples == sum over columns of value x samples-per-column)
+    notes = PR.NoteBatch(*bench.make_notes(256, 99), device=gpu)
+    roll, onoff, row_off, _ = PR.rasterize(notes, bench.ROLL_FS)
+    up, so = PR.upsample(roll, row_off, bench.CLIP_LEN, bench.ROLL_FS, bench.SR, 21, 88, torch.int8)
+    up = up.view(256, 88, bench.CLIP_LEN)
+    cols = (torch.arange(bench.CLIP_LEN, device=gpu) * bench.ROLL_FS) // bench.SR
+    ro = row_off.cpu().numpy()
+    for i in (0, 17, 255):
+        T = int(ro[i + 1] - ro[i])
+        per_col = torch.bincount(cols[cols < T], minlength=T).to(torch.int64)
+        want = (roll[ro[i]:ro[i + 1], 21:109].to(torch.int64) * per_col[:, None]).sum(0)
+        assert torch.equal(up[i].to(torch.int64).sum(-1), want)
+    # (5) Griffin-Lim at scale is a fixed point on consistent spectrograms: true phase in, 2 iterations, signal back
+    nb = 256
+    gb = F.ClipBatch.from_frames([bench.T_FRAMES] * nb, bench.HOP, device=gpu)
+    b2 = F.ClipBatch.uniform(nb, bench.HOP * (bench.T_FRAMES - 1), bench.HOP, clip_stride=bench.CLIP_LEN, device=gpu)
+    D = F.stft_batch(audio, b2, "complex")
+    ph = ((torch.angle(D) / (2 * np.pi)) % 1.0).float().contiguous()
+    y = F.griffinlim_batch(D.abs().contiguous(), gb, n_iter=2, init_phase=ph, layout=F.FRAME_MAJOR).view(nb, -1)
+    ref = audio.view(n, -1)[:nb, :y.shape[1]]
+    assert (y - ref)[:, 2048:-2048].abs().max() < 2e-3
