@@ -68,7 +68,7 @@ def build_cuda(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [_nvcc(), "-shared", "-o", LIB_CUDA] + objs + ["-cudart", "static"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_CUDA] + objs + ["-cudart", "static"]
     subprocess.check_call(cmd)
     _write_stamp(LIB_CUDA, stamp)
     return LIB_CUDA
