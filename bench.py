@@ -313,7 +313,7 @@ def run_ours(args):
         if e2e is not None:
             line["e2e"] = e2e
             line["e2e_planes_to_host"] = e2e_all
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline(cores=1, budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
     if world > 1:
