@@ -361,6 +361,7 @@ def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrie
             batch=F.ClipBatch.uniform(m, CLIP_LEN, HOP, device=device),
             gl_batch=F.ClipBatch.from_frames([T_FRAMES] * m, HOP, device=device),
             notes=[t[n0:n1] for t in h_notes],
+            h_max_end=np.array([notes_h[3][no[i]:no[i + 1]].max() for i in range(a0, a1)], dtype=np.float64),
             noff=torch.from_numpy(np.ascontiguousarray(no[a0:a1 + 1] - no[a0])).pin_memory()))
     streams = [torch.cuda.Stream(device=device) for _ in range(2)]
     d2h_roll = [0]
@@ -380,7 +381,7 @@ def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrie
                 nb.device = device
                 nb.pitch, nb.velocity, nb.start, nb.end = [t.to(device, non_blocking=True) for t in ch["notes"]]
                 nb.note_offsets = ch["noff"].to(device, non_blocking=True)
-                nb.n_pieces, nb.end_times, nb.pedals = m, None, None
+                nb.n_pieces, nb.end_times, nb.pedals, nb.h_max_end = m, None, None, ch["h_max_end"]
                 roll, onoff, row_off, _ = PR.rasterize(nb, ROLL_FS)
                 rows = min(roll.shape[0], m * rows_per_clip)
                 r0 = a0 * rows_per_clip

@@ -24,8 +24,13 @@ class NoteBatch:
         self.velocity = torch.as_tensor(np.asarray(velocity, dtype=np.int32)).to(device)
         self.start = torch.as_tensor(np.asarray(start, dtype=np.float64)).to(device)
         self.end = torch.as_tensor(np.asarray(end, dtype=np.float64)).to(device)
-        self.note_offsets = torch.as_tensor(np.asarray(note_offsets, dtype=np.int64)).to(device)
+        h_off = np.asarray(note_offsets, dtype=np.int64)
+        h_end = np.asarray(end, dtype=np.float64)
+        self.note_offsets = torch.as_tensor(h_off).to(device)
         self.n_pieces = int(self.note_offsets.numel()) - 1
+        # host copies of what the roll geometry needs (latest note end per piece), so that rasterize() never has to
+        # read a size back from the device
+        self.h_max_end = np.array([h_end[a:b].max() if b > a else 0.0 for a, b in zip(h_off[:-1], h_off[1:])], dtype=np.float64)
         if self.n_pieces < 1:
             raise ValueError("note_offsets needs at least two entries")
         # optional per-piece extras of a parsed MIDI file: latest event time (pretty_midi get_end_time also counts
@@ -68,13 +73,19 @@ def rasterize(notes, fs, want_velsum=False, pedal_threshold=64):
     pretty_midi >= 0.2.9 (``pedal_threshold``, None = off) is applied before binarising.
     """
     o = _lib.ops()
-    if notes.end_times is None:
+    h_end = notes.end_times if notes.end_times is not None else getattr(notes, "h_max_end", None)
+    if h_end is not None:
+        # int(fs * end_time) on the host is the same IEEE double product the device kernel evaluates
+        h_rows = np.array([max(0, int(fs * float(t))) for t in h_end], dtype=np.int64)
+        h_ro = np.zeros(notes.n_pieces + 1, dtype=np.int64)
+        np.cumsum(h_rows, out=h_ro[1:])
+        row_offsets = torch.from_numpy(h_ro).pin_memory().to(notes.device, non_blocking=True)
+        total_rows = int(h_ro[-1])
+    else:  # device-only note arrays: count on the device, one small read-back to size the roll
         rows = o.pianoroll_count_rows(notes.end, notes.note_offsets, int(fs))
-    else:
-        rows = torch.tensor([int(fs * t) for t in notes.end_times], dtype=torch.int64, device=notes.device)
-    row_offsets = torch.zeros(notes.n_pieces + 1, dtype=torch.int64, device=notes.device)
-    torch.cumsum(rows, 0, out=row_offsets[1:])
-    total_rows = int(row_offsets[-1].item())  # one small D2H: the roll has to be allocated
+        row_offsets = torch.zeros(notes.n_pieces + 1, dtype=torch.int64, device=notes.device)
+        torch.cumsum(rows, 0, out=row_offsets[1:])
+        total_rows = int(row_offsets[-1].item())
     sp = ss = se = None
     if notes.pedals is not None and pedal_threshold is not None:
         spans = [(i, a, b) for i, ev in enumerate(notes.pedals) for a, b in pedal_spans(ev, fs, pedal_threshold) if b > a]
@@ -107,10 +118,14 @@ def upsample(plane, row_offsets, samples_per_piece, fs, sr, pitch_lo=21, n_keys=
     Returns (flat tensor, sample_offsets); piece p's block is flat[n_keys*off[p] : n_keys*off[p+1]].view(n_keys, N_p).
     """
     n_pieces = int(row_offsets.numel()) - 1
-    spp = np.broadcast_to(np.asarray(samples_per_piece, dtype=np.int64), (n_pieces,))
-    so = np.zeros(n_pieces + 1, dtype=np.int64)
-    np.cumsum(spp, out=so[1:])
-    sample_offsets = torch.from_numpy(so).to(plane.device)
+    if np.ndim(samples_per_piece) == 0:  # uniform pieces: offsets built on the device, nothing crosses PCIe
+        so = np.arange(n_pieces + 1, dtype=np.int64) * int(samples_per_piece)
+        sample_offsets = torch.arange(n_pieces + 1, dtype=torch.int64, device=plane.device) * int(samples_per_piece)
+    else:
+        spp = np.asarray(samples_per_piece, dtype=np.int64)
+        so = np.zeros(n_pieces + 1, dtype=np.int64)
+        np.cumsum(spp, out=so[1:])
+        sample_offsets = torch.from_numpy(so).pin_memory().to(plane.device, non_blocking=True)
     out = _lib.ops().pianoroll_upsample(plane, row_offsets, sample_offsets, int(so[-1]), int(fs), int(sr), int(pitch_lo),
                                         int(n_keys), DTYPE_CODES[dtype])
     return out, so
