@@ -1,8 +1,10 @@
-// P1 / P2: framing + Hann window + 2048-point real FFT with the magnitude / power / log1p / mel epilogue
-// fused in.  One warp per frame, persistent CTAs of 8 warps walking tiles of 8 consecutive frames of one clip.
+// P1 / P2: framing + Hann window + 2048-point real FFT with the epilogue fused in: complex spectrum, magnitude, power,
+// log1p(power), or -- for the mel path -- the power spectrum as split-precision bf16 (hi, lo) rows handed to the
+// tcgen05 projection kernel in mel_gemm.cu through an L2-resident ring.  One warp per frame, persistent CTAs of
+// 8 warps walking tiles of 8 consecutive frames of one clip.
 //
-// Replaces librosa.stft + np.log1p(np.abs(.)**2) (reference preprocessing/preprocess.py:47-57) and
-// librosa.feature.melspectrogram (reference tests/plot_spec.py:20).
+// Replaces librosa.stft + np.log1p(np.abs(.)**2) (reference preprocessing/preprocess.py:47-57) and, together with
+// mel_gemm.cu, librosa.feature.melspectrogram (reference tests/plot_spec.py:20).
 #include <algorithm>
 #include <vector>
 #include "fft_warp.cuh"
