@@ -75,37 +75,57 @@ constexpr int kSlot = 2 * kScratchPerWarp;  // floats between consecutive frame 
 
 // Overlap-add of one tile when hop divides n_fft (R = n_fft / hop frames overlap every sample): thread j walks the
 // span hop-block by hop-block; block b receives frames f = b-R+1 .. b, summed in increasing f.
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  // one 128-bit reduction instead of four 32-bit ones (sm_90+): the atomic path is LSU-issue bound per lane
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Overlap-add of one tile when hop divides n_fft (R = n_fft / hop frames overlap every sample).  The span is walked
+// hop-block by hop-block, four samples per thread; block b receives frames f = b-R+1 .. b, summed in increasing f.
+// Blocks b < R-1 are shared with the previous tile of the clip and blocks b >= nvalid with the next one: those go to
+// the accumulator as 128-bit reductions (the buffer was zeroed one launch earlier); every other block belongs to this
+// tile alone and is written with a plain 128-bit store -- no read-modify-write in L2 and nothing to zero.
 template <int R>
-__device__ __forceinline__ void ola_blocks(const float* s_slots, int nvalid, int hop, int hop_shift, float* dst) {
+__device__ __forceinline__ void ola_blocks(const float* s_slots, int nvalid, int hop_shift, bool first, bool last,
+                                           float* dst) {
   const int n_blocks = nvalid - 1 + R;
-  for (int j = threadIdx.x; j < hop; j += blockDim.x) {
+  const int q_shift = hop_shift - 2;  // float4 items per hop block = 2^q_shift (hop is a power of two >= 128 here)
+  const int items = n_blocks << q_shift;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int b = it >> q_shift, j = (it & ((1 << q_shift) - 1)) << 2;
     const float* sp = s_slots + j;
-    float* dp = dst + j;
-    for (int b = 0; b < n_blocks; ++b) {
-      float sum = 0.0f;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int r = R - 1; r >= 0; --r) {
-        const int f = b - r;
-        if (f >= 0 && f < nvalid) sum += sp[f * kSlot + (r << hop_shift)];
+    for (int r = R - 1; r >= 0; --r) {  // increasing frame index f = b - r
+      const int f = b - r;
+      if (f >= 0 && f < nvalid) {
+        const float4 v = *reinterpret_cast<const float4*>(sp + f * kSlot + (r << hop_shift));
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
       }
-      atomicAdd(dp + (b << hop_shift), sum);
     }
+    float* p = dst + (b << hop_shift) + j;
+    const bool shared = (!first && b < R - 1) || (!last && b >= nvalid);
+    if (shared) red_add_v4(p, sum);
+    else *reinterpret_cast<float4*>(p) = sum;
   }
 }
 
-// Sum the tile's frame slots in frame order and add the span to the global accumulator; zero the next accumulator.
+// Sum the tile's frame slots in frame order and add the span to the global accumulator; zero, in the accumulator of
+// the NEXT launch, the region this tile shares with its successor.
 __device__ __forceinline__ void overlap_add_tile(const float* s_slots, const ClipDesc& cd, int t0, int hop, int hop_shift,
                                                  float* __restrict__ acc_out, float* __restrict__ acc_zero) {
   const int nvalid = min(kWarpsPerCta, cd.frames - t0);
+  const bool first = t0 == 0, last = t0 + kWarpsPerCta >= cd.frames;
   float* dst = acc_out + cd.acc_offset + (int64_t)t0 * hop;
+  const bool blocks = hop_shift >= 7 && hop_shift <= 10;
   if (hop_shift == 9) {
-    ola_blocks<4>(s_slots, nvalid, hop, hop_shift, dst);
+    ola_blocks<4>(s_slots, nvalid, hop_shift, first, last, dst);
   } else if (hop_shift == 8) {
-    ola_blocks<8>(s_slots, nvalid, hop, hop_shift, dst);
+    ola_blocks<8>(s_slots, nvalid, hop_shift, first, last, dst);
   } else if (hop_shift == 10) {
-    ola_blocks<2>(s_slots, nvalid, hop, hop_shift, dst);
+    ola_blocks<2>(s_slots, nvalid, hop_shift, first, last, dst);
   } else if (hop_shift == 7) {
-    ola_blocks<16>(s_slots, nvalid, hop, hop_shift, dst);
+    ola_blocks<16>(s_slots, nvalid, hop_shift, first, last, dst);
   } else {
     const int span = (nvalid - 1) * hop + kNfft;
     for (int p = threadIdx.x; p < span; p += blockDim.x) {
@@ -118,15 +138,18 @@ __device__ __forceinline__ void overlap_add_tile(const float* s_slots, const Cli
     }
   }
   if (acc_zero) {
-    const int64_t acc_len = kNfft + (int64_t)hop * (cd.frames - 1);
-    const int64_t z0 = (int64_t)t0 * hop;
-    const bool last = t0 + kWarpsPerCta >= cd.frames;
-    const int64_t z1 = last ? acc_len : z0 + (int64_t)kWarpsPerCta * hop;
     float* z = acc_zero + cd.acc_offset;
-    if (((z0 | z1) & 3) == 0) {  // accumulators are 16-byte aligned per clip
-      float4* z4 = reinterpret_cast<float4*>(z);
-      for (int64_t p = (z0 >> 2) + threadIdx.x; p < (z1 >> 2); p += blockDim.x) z4[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (blocks) {
+      // only the region shared with the next tile is accumulated by two tiles: [(t0+nv)*hop, (t0+nv)*hop + n_fft - hop)
+      if (!last) {
+        const int64_t z0 = (int64_t)(t0 + nvalid) * hop, z1 = z0 + kNfft - hop;
+        float4* z4 = reinterpret_cast<float4*>(z);
+        for (int64_t p = (z0 >> 2) + threadIdx.x; p < (z1 >> 2); p += blockDim.x) z4[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     } else {
+      const int64_t acc_len = kNfft + (int64_t)hop * (cd.frames - 1);
+      const int64_t z0 = (int64_t)t0 * hop;
+      const int64_t z1 = last ? acc_len : z0 + (int64_t)kWarpsPerCta * hop;
       for (int64_t p = z0 + threadIdx.x; p < z1; p += blockDim.x) z[p] = 0.0f;
     }
   }
@@ -136,10 +159,16 @@ constexpr size_t kGlSmemBytes = 8192 + sizeof(float2) * kTwpCount + 8192 + 8192 
 constexpr int kSpecStride = 1032;  // float2 elements per tprev row: 8256 B, 16-byte aligned rows for cp.async
 
 __device__ __forceinline__ float unit_scale(float ax, float ay) {
-  // 1 / (|a| + 1e-16) without a branch: |a| = m2 * rsqrt(m2) (guarded at 0), then one reciprocal
-  const float m2 = fmaf(ax, ax, ay * ay);
-  const float mag = m2 * rsqrtf(fmaxf(m2, 1e-37f));
-  return __fdividef(1.0f, mag + 1e-16f);
+  // librosa: angles /= |angles| + 1e-16.  1 / (|a| + 1e-16) and rsqrt(|a|^2 + 1e-32) agree to float32 precision for
+  // every |a| that is not itself ~1e-16 (where S * angles is inaudible either way), and both map a = 0 to 0.
+  return rsqrtf(fmaf(ax, ax, fmaf(ay, ay, 1e-32f)));
+}
+
+// streaming read that does not displace the overlap-add accumulator lines from L1
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
 }
 
 template <bool INIT, bool FIRST>
@@ -160,20 +189,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
   stage_table(s_wsyn, P.tabs.wsyn, 512);
   __syncthreads();
 
+  int c = blockIdx.x < P.total_tiles ? __ldg(P.tile_clip + blockIdx.x) : 0;
+  ClipDesc cd = P.clips[c];
   for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-    const int c = __ldg(P.tile_clip + tile);
-    const ClipDesc cd = P.clips[c];
     const int t0 = (tile - cd.tile_offset) * kWarpsPerCta;
     const int t = t0 + warp;
     const bool active = t < cd.frames;
-    if (!INIT && warp == 0) {  // pull the accumulator span of this CTA's next tile towards L2
-      const int nt = tile + gridDim.x;
-      if (nt < P.total_tiles) {
-        const ClipDesc cn = P.clips[__ldg(P.tile_clip + nt)];
-        const float* a = P.acc_in + cn.acc_offset + (int64_t)(nt - cn.tile_offset) * kWarpsPerCta * P.hop;
-        const int span = (kWarpsPerCta - 1) * P.hop + kNfft;
-        for (int i = lane * 32; i < span; i += 32 * 32) prefetch_l2(a + i);
-      }
+    // descriptor of this CTA's next tile: fetched now (one tile ahead), used at the bottom of the loop
+    const int nt = tile + gridDim.x;
+    const int c_next = nt < P.total_tiles ? __ldg(P.tile_clip + nt) : c;
+    const ClipDesc cd_next = P.clips[c_next];
+    if (!INIT && warp == 0 && nt < P.total_tiles) {  // pull the accumulator span of the next tile towards L2
+      const float* a = P.acc_in + cd_next.acc_offset + (int64_t)(nt - cd_next.tile_offset) * kWarpsPerCta * P.hop;
+      const int span = (kWarpsPerCta - 1) * P.hop + kNfft;
+      for (int i = lane * 32; i < span; i += 32 * 32) prefetch_l2(a + i);
     }
     if (active) {
       const int64_t frame = cd.frame_offset + t;
@@ -272,7 +301,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
         for (int g8 = 0; g8 < 32; g8 += 8) {
           float sm[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sm[i] = __ldg((g8 < 16 ? SA : SB) + 32 * (g8 + i));
+          for (int i = 0; i < 8; ++i) sm[i] = ld_stream((g8 < 16 ? SA : SB) + 32 * (g8 + i));
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int j = g8 + i;
@@ -289,7 +318,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
           if (!FIRST) tp = scratch[512];
           trow[512] = mid;
           const float ax = fmaf(-P.alpha, tp.x, mid.x), ay = fmaf(-P.alpha, tp.y, mid.y);
-          const float sc = __ldg(Srow + 512) * unit_scale(ax, ay);
+          const float sc = ld_stream(Srow + 512) * unit_scale(ax, ay);
           mid = make_float2(sc * ax, sc * ay);
         }
         __syncwarp();  // everyone is done reading the staged previous iterate before the inverse FFT reuses the tile
@@ -299,6 +328,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
     __syncthreads();
     overlap_add_tile(reinterpret_cast<const float*>(s_scratch_all), cd, t0, P.hop, P.hop_shift, P.acc_out, P.acc_zero);
     __syncthreads();
+    c = c_next;
+    cd = cd_next;
   }
 }
 
