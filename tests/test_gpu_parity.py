@@ -114,6 +114,37 @@ def test_stft_ragged_batch_device_tensors(pkg, gpu):
     assert f0 == b.total_frames
 
 
+def test_raw_c_abi_through_ctypes(pkg, gpu):
+    """The boundary itself: include/mst_b200.h bound with ctypes (no torch op in between), as INTEGRATION.md shows."""
+    import ctypes
+    lib = pkg._lib.cdll()
+    lib.mst_batch_total_frames.restype = ctypes.c_int64
+    vp = ctypes.c_void_p
+    y = clip(14, 50000, "noise")
+    a = torch.from_numpy(y).to(gpu)
+    offs = (ctypes.c_int64 * 2)(0, 20000)
+    lens = (ctypes.c_int64 * 2)(30000, 30000)
+    batch = vp()
+    assert lib.mst_batch_create(2, offs, lens, 2048, 256, 0, ctypes.byref(batch)) == 0, lib.mst_last_error()
+    frames = lib.mst_batch_total_frames(batch)
+    assert frames == 2 * (1 + 30000 // 256)
+    out = torch.empty(frames * 1025, dtype=torch.float32, device=gpu)
+    stream = vp(torch.cuda.current_stream().cuda_stream)
+    n0 = lib.mst_launch_count()
+    assert lib.mst_stft_f32(vp(a.data_ptr()), batch, 3, 1, vp(out.data_ptr()), stream) == 0, lib.mst_last_error()
+    assert lib.mst_launch_count() == n0 + 1
+    torch.cuda.synchronize()
+    T = frames // 2
+    for c, o in enumerate((0, 20000)):
+        ref = np.log1p(np.abs(ostft.stft(y[o:o + 30000], 2048, 256, out_dtype=np.complex128)) ** 2)
+        assert_close(out[c * T * 1025:(c + 1) * T * 1025].view(1025, T).cpu().numpy(), ref)
+    # error reporting: bad layout, null pointer
+    assert lib.mst_stft_f32(vp(a.data_ptr()), batch, 3, 7, vp(out.data_ptr()), stream) == -1
+    assert b"layout" in lib.mst_last_error()
+    assert lib.mst_stft_f32(None, batch, 3, 1, vp(out.data_ptr()), stream) == -1
+    lib.mst_batch_destroy(batch)
+
+
 # ---- P2: mel ----------------------------------------------------------------------------------
 @pytest.mark.parametrize("sr,hop", [(22050, 512), (44100, 256)])
 def test_melspectrogram_and_logmel(pkg, sr, hop):
