@@ -268,6 +268,26 @@ def run_ours(args):
         single = {"logmel_hop512_ms": t_lm, "log1p_power_hop256_ms": t_lp, "griffinlim32_hop512_ms": t_gl,
                   "griffinlim32_audio_s_per_s": 30.0 / (t_gl * 1e-3), "frames": T30}
 
+    # ---- "next" rows and the reference's own geometry: measured, not part of `value` -------------------------
+    extras = None
+    if rank == 0 and not args.no_single:
+        from ml_music_style_transfer_b200 import _lib as L
+        x44 = torch.randn(64 * 8 * 44100, device=device) * 0.1           # 64 clips x 8 s at 44.1 kHz, one buffer
+        t_rs = med(timed(lambda: L.ops().resample(x44, 44100, 22050), 5))
+        taps = 2 * 64 * 2                                                 # both wings, 64 zero crossings, ratio 1/2
+        n_ch, step_, clen = 256, 131072, 219904                           # preprocess.py:66-67 chunk geometry
+        a_repo = torch.randn((n_ch - 1) * step_ + clen, device=device) * 0.1
+        b_repo = F.ClipBatch.uniform(n_ch, clen, 256, clip_stride=step_, device=device)
+        t_repo = med(timed(lambda: F.stft_batch(a_repo, b_repo, "log1p_power", F.BIN_MAJOR), 5))
+        repo_bytes = n_ch * 4 * clen + 4 * K * b_repo.total_frames
+        extras = {
+            "resample_44k1_to_22k05": {"ms": t_rs, "audio_s_per_s": 64 * 8 / (t_rs * 1e-3),
+                                       "gflops": 2.0 * taps * 2 * (x44.numel() // 2) / (t_rs * 1e-3) / 1e9},
+            "reference_geometry_log1p_power": {"chunks": n_ch, "ms": t_repo, "audio_s_per_s": n_ch * clen / 44100 / (t_repo * 1e-3),
+                                               "hbm_frac": repo_bytes / (t_repo * 1e-3) / 1e9 / hbm_peak,
+                                               "note": "44.1 kHz, hop 256, 219904-sample chunks every 131072, bin-major stack"}}
+        del x44, a_repo
+
     # ---- e2e: NumPy-facing API with pinned host buffers ------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -310,6 +330,7 @@ def run_ours(args):
         }
         if not args.no_single:
             line["single_clip_30s"] = single
+            line["extras"] = extras
         if e2e is not None:
             line["e2e"] = e2e
             line["e2e_planes_to_host"] = e2e_all

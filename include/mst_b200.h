@@ -94,8 +94,8 @@ int mst_stft_f32(const float* d_audio, const mst_batch_t* batch, int out_mode, i
  * P2: mel filterbank + projection.
  * mst_mel_filterbank_f32 replaces librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False,
  * norm='slaney') (float64 maths, float32 result, [n_mels][1+n_fft/2] row-major, host memory).
- * A mel plan owns the device copies of a filterbank (dense, banded-compact and split-precision
- * forms).  mst_stft_mel_f32 replaces librosa.feature.melspectrogram(y=, sr=, n_fft=, hop_length=)
+ * A mel plan owns the device form of a filterbank: its non-zero band per 64-bin slice, split into
+ * bf16 (hi, lo) and stored as the shared-memory image the tcgen05 projection kernel consumes.  mst_stft_mel_f32 replaces librosa.feature.melspectrogram(y=, sr=, n_fft=, hop_length=)
  * [plot_spec.py:20; preprocess.py:55] = mel_basis @ |stft|^2, with optional log1p (this build's
  * "log-mel", following the log1p convention of preprocess.py:49).
  * d_out: FRAME_MAJOR [total_frames][n_mels] or BIN_MAJOR per clip [n_mels][T_c].

@@ -22,7 +22,6 @@ struct MelSlices {      // per 64-bin K-slice: the band of mel rows that is non-
 
 struct mst_mel_plan {
   int n_mels = 0, n_bins = 0;
-  float* d_dense = nullptr;            // [n_mels][n_bins] float32 filterbank as given
   mst::MelSlices slices{};
   int w_rows = 0;                      // sum of slices.n
   __nv_bfloat16* d_band_hi = nullptr;  // [w_rows][64] bf16(W)

@@ -291,9 +291,7 @@ int mst_mel_plan_create(const float* W, int n_mels, int n_bins, mst_mel_plan_t**
     lo.swap(il);
   }
   const size_t band_bytes = std::max<size_t>(1, hi.size()) * sizeof(__nv_bfloat16);
-  if (cudaMalloc(&p->d_dense, sizeof(float) * (size_t)n_mels * n_bins) != cudaSuccess ||
-      cudaMalloc(&p->d_band_hi, band_bytes) != cudaSuccess || cudaMalloc(&p->d_band_lo, band_bytes) != cudaSuccess ||
-      cudaMemcpy(p->d_dense, W, sizeof(float) * (size_t)n_mels * n_bins, cudaMemcpyHostToDevice) != cudaSuccess ||
+  if (cudaMalloc(&p->d_band_hi, band_bytes) != cudaSuccess || cudaMalloc(&p->d_band_lo, band_bytes) != cudaSuccess ||
       cudaMemcpy(p->d_band_hi, hi.data(), hi.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(p->d_band_lo, lo.data(), lo.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice) != cudaSuccess) {
     mst_mel_plan_destroy(p);
@@ -309,7 +307,6 @@ int mst_mel_plan_create(const float* W, int n_mels, int n_bins, mst_mel_plan_t**
 
 void mst_mel_plan_destroy(mst_mel_plan_t* p) {
   if (!p) return;
-  if (p->d_dense) cudaFree(p->d_dense);
   if (p->d_band_hi) cudaFree(p->d_band_hi);
   if (p->d_band_lo) cudaFree(p->d_band_lo);
   delete p;

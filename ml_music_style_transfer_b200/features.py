@@ -74,6 +74,13 @@ class ClipBatch:
             _lib.ops().batch_destroy(self.handle)
             self.handle = 0
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def __del__(self):
         try:
             self.close()
@@ -134,18 +141,16 @@ def stft(y, n_fft=N_FFT, hop_length=None, win_length=None, window="hann", center
         raise NotImplementedError("center=False is not used by the reference")
     hop = n_fft // 4 if hop_length is None else int(hop_length)
     a, was_np = _to_device_audio(y)
-    b = ClipBatch.uniform(1, a.numel(), hop, pad_mode=pad_mode, device=a.device)
-    out = stft_batch(a, b, "complex").t()  # (1025, T) view over [T][1025] memory == Fortran order
-    b.close()
+    with ClipBatch.uniform(1, a.numel(), hop, pad_mode=pad_mode, device=a.device) as b:
+        out = stft_batch(a, b, "complex").t()  # (1025, T) view over [T][1025] memory == Fortran order
     return out.cpu().numpy() if was_np else out
 
 
 def spectrogram(y, hop_length, out="log1p_power", pad_mode="reflect"):
     """(1025, T) float32 epilogue of the STFT for one clip (Fortran-ordered view)."""
     a, was_np = _to_device_audio(y)
-    b = ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device)
-    o = stft_batch(a, b, out).view(b.total_frames, N_BINS).t()
-    b.close()
+    with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device) as b:
+        o = stft_batch(a, b, out).view(b.total_frames, N_BINS).t()
     return o.cpu().numpy() if was_np else o
 
 
@@ -155,9 +160,8 @@ def melspectrogram(y=None, sr=22050, n_fft=N_FFT, hop_length=512, n_mels=128, fm
     _check_window("hann", None, n_fft)
     a, was_np = _to_device_audio(y)
     plan = MelPlan.get(sr, n_fft, n_mels, fmin, fmax, a.device)
-    b = ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device)
-    o = melspectrogram_batch(a, b, plan, log1p=log1p, layout=BIN_MAJOR).view(n_mels, b.total_frames)
-    b.close()
+    with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device) as b:
+        o = melspectrogram_batch(a, b, plan, log1p=log1p, layout=BIN_MAJOR).view(n_mels, b.total_frames)
     return o.cpu().numpy() if was_np else o
 
 
@@ -180,7 +184,9 @@ def griffinlim(S, n_iter=32, hop_length=None, win_length=None, window="hann", mo
     """librosa.griffinlim drop-in for one (1025, T) magnitude spectrogram -> float32 waveform of hop*(T-1) samples.
 
     ``random_state=int`` reproduces librosa's ``RandomState(seed).rand(*S.shape)`` initial phase exactly (drawn on the
-    host); ``init_phase`` supplies the uniform [0,1) field directly; otherwise the phase comes from the device RNG.
+    host); ``init_phase`` supplies the uniform [0,1) field directly; with ``random_state=None`` the phase comes from the
+    device's counter-based RNG, seeded from NumPy's global generator (the generator librosa itself would draw from, so
+    ``np.random.seed`` makes runs repeatable here too).
     """
     was_np = not isinstance(S, torch.Tensor)
     device = _lib.require_cuda(None if was_np else S.device)
@@ -203,10 +209,9 @@ def griffinlim(S, n_iter=32, hop_length=None, win_length=None, window="hann", mo
     else:
         layout, S_flat = BIN_MAJOR, S.contiguous()
         ph = None if init_phase is None else init_phase.to(torch.float32).contiguous()
-    b = ClipBatch.from_frames([T], hop, pad_mode=pad_mode, device=device)
-    y = griffinlim_batch(S_flat.to(torch.float32), b, n_iter, momentum, ph, init, 0 if random_state is None else 0,
-                         layout)
-    b.close()
+    seed = int(np.random.randint(0, 2 ** 31 - 1))
+    with ClipBatch.from_frames([T], hop, pad_mode=pad_mode, device=device) as b:
+        y = griffinlim_batch(S_flat.to(torch.float32), b, n_iter, momentum, ph, init, seed, layout)
     return y.cpu().numpy() if was_np else y
 
 

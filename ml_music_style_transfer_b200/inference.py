@@ -61,9 +61,8 @@ class AudioSynthesizer():
             ph = init_phase if isinstance(init_phase, torch.Tensor) else \
                 torch.from_numpy(np.ascontiguousarray(init_phase, dtype=np.float32)).to(device)
             ph = ph.to(torch.float32).contiguous()
-        b = features.ClipBatch.from_frames([T], int(hop_length), device=device)
-        y = features.griffinlim_batch(S.contiguous(), b, n_iter=n_iter, momentum=0.99, init_phase=ph, init="random",
-                                      seed=0 if audio_id is None else hash(str(audio_id)) & 0x7FFFFFFF,
-                                      layout=features.BIN_MAJOR, is_log1p_power=True)
-        b.close()
+        seed = int(np.random.randint(0, 2 ** 31 - 1))  # librosa draws from NumPy's global generator too
+        with features.ClipBatch.from_frames([T], int(hop_length), device=device) as b:
+            y = features.griffinlim_batch(S.contiguous(), b, n_iter=n_iter, momentum=0.99, init_phase=ph, init="random",
+                                          seed=seed, layout=features.BIN_MAJOR, is_log1p_power=True)
         return y.cpu().numpy() if was_np else y

@@ -61,10 +61,9 @@ def process_audio_into_chunks(audio, style, song_id, num_chunks, debug=False):
     if last_end > a.numel():
         # the reference silently produces ragged chunks here and np.array() then fails / makes an object array
         raise ValueError(f"audio has {a.numel()} samples but {num_chunks} chunks need {last_end}")
-    b = features.ClipBatch.uniform(num_chunks, n_samples_per_chunk, hp.ws, clip_stride=step, device=a.device)
-    T = b.total_frames // num_chunks
-    out = features.stft_batch(a, b, "log1p_power", features.BIN_MAJOR).view(num_chunks, features.N_BINS, T)
-    b.close()
+    with features.ClipBatch.uniform(num_chunks, n_samples_per_chunk, hp.ws, clip_stride=step, device=a.device) as b:
+        T = b.total_frames // num_chunks
+        out = features.stft_batch(a, b, "log1p_power", features.BIN_MAJOR).view(num_chunks, features.N_BINS, T)
     return out.cpu().numpy() if was_np else out
 
 
