@@ -171,39 +171,46 @@ __device__ __forceinline__ float ld_stream(const float* p) {
   return v;
 }
 
-template <bool INIT, bool FIRST>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* s_tw1024 = reinterpret_cast<float2*>(smem_raw);
-  float2* s_twp = s_tw1024 + 1024;
-  float* s_wq = reinterpret_cast<float*>(s_twp + kTwpCount);
-  float* s_wsyn = s_wq + kNfft;
-  float2* s_scratch_all = reinterpret_cast<float2*>(s_wsyn + kNfft);
+// Shared-memory views of one CTA (tables staged once, one scratch tile per warp).
+struct GlSmem {
+  float2* tw1024;
+  float2* twp;
+  float* wq;
+  float* wsyn;
+  float2* scratch_all;
+};
+
+__device__ __forceinline__ GlSmem gl_smem_setup(unsigned char* smem_raw, const GlParams& P) {
+  GlSmem m;
+  m.tw1024 = reinterpret_cast<float2*>(smem_raw);
+  m.twp = m.tw1024 + 1024;
+  m.wq = reinterpret_cast<float*>(m.twp + kTwpCount);
+  m.wsyn = m.wq + kNfft;
+  m.scratch_all = reinterpret_cast<float2*>(m.wsyn + kNfft);
+  stage_table(m.tw1024, P.tabs.tw1024, 512);
+  stage_table(m.twp, P.tabs.twp, kTwpCount / 2);
+  stage_table(m.wq, P.wq, 512);
+  stage_table(m.wsyn, P.tabs.wsyn, 512);
+  __syncthreads();
+  return m;
+}
+
+// One tile (8 consecutive frames of clip c, one warp each) of one launch: synthesis only (INIT) or re-analysis ->
+// re-projection -> synthesis, then the tile's overlap-add.  COHERENT: accumulator reads bypass L1 (needed when several
+// iterations run inside one persistent kernel and another SM wrote the accumulator since this SM last read it).
+template <bool INIT, bool FIRST, bool COHERENT>
+__device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int c, const ClipDesc& cd, int tile) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = mirror_base(lane);
-  float2* scratch = s_scratch_all + warp * kScratchPerWarp;
-
-  stage_table(s_tw1024, P.tabs.tw1024, 512);
-  stage_table(s_twp, P.tabs.twp, kTwpCount / 2);
-  stage_table(s_wq, P.wq, 512);
-  stage_table(s_wsyn, P.tabs.wsyn, 512);
-  __syncthreads();
-
-  int c = blockIdx.x < P.total_tiles ? __ldg(P.tile_clip + blockIdx.x) : 0;
-  ClipDesc cd = P.clips[c];
-  for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-    const int t0 = (tile - cd.tile_offset) * kWarpsPerCta;
-    const int t = t0 + warp;
-    const bool active = t < cd.frames;
-    // descriptor of this CTA's next tile: fetched now (one tile ahead), used at the bottom of the loop
-    const int nt = tile + gridDim.x;
-    const int c_next = nt < P.total_tiles ? __ldg(P.tile_clip + nt) : c;
-    const ClipDesc cd_next = P.clips[c_next];
-    if (!INIT && warp == 0 && nt < P.total_tiles) {  // pull the accumulator span of the next tile towards L2
-      const float* a = P.acc_in + cd_next.acc_offset + (int64_t)(nt - cd_next.tile_offset) * kWarpsPerCta * P.hop;
-      const int span = (kWarpsPerCta - 1) * P.hop + kNfft;
-      for (int i = lane * 32; i < span; i += 32 * 32) prefetch_l2(a + i);
-    }
+  float2* scratch = m.scratch_all + warp * kScratchPerWarp;
+  float2* s_tw1024 = m.tw1024;
+  float2* s_twp = m.twp;
+  float* s_wq = m.wq;
+  float* s_wsyn = m.wsyn;
+  float2* s_scratch_all = m.scratch_all;
+  const int t0 = (tile - cd.tile_offset) * kWarpsPerCta;
+  const int t = t0 + warp;
+  const bool active = t < cd.frames;
     if (active) {
       const int64_t frame = cd.frame_offset + t;
       const float* Srow = P.S + frame * kBins;
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
           const float2* w2 = reinterpret_cast<const float2*>(s_wq) + lane;
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
-            const float2 a = a2[32 * r];
+            const float2 a = COHERENT ? __ldcg(a2 + 32 * r) : a2[32 * r];
             const float2 w = w2[32 * r];
             v[r] = make_float2(a.x * w.x, a.y * w.y);
           }
@@ -268,7 +275,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
             } else if (n >= L) {
               if (P.pad_mode == MST_PAD_REFLECT) n = 2 * (L - 1) - n; else ok = false;
             }
-            sf[jj] = ok ? acc[n + kHalf] * __ldg(iw + n + kHalf) * __ldg(P.tabs.window + jj) : 0.0f;
+            sf[jj] = ok ? (COHERENT ? __ldcg(acc + n + kHalf) : acc[n + kHalf]) * __ldg(iw + n + kHalf) * __ldg(P.tabs.window + jj) : 0.0f;
           }
           __syncwarp();
 #pragma unroll
@@ -330,8 +337,82 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
     __syncthreads();
     overlap_add_tile(reinterpret_cast<const float*>(s_scratch_all), cd, t0, P.hop, P.hop_shift, P.acc_out, P.acc_zero);
     __syncthreads();
+}
+
+template <bool INIT, bool FIRST>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const GlSmem m = gl_smem_setup(smem_raw, P);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int c = blockIdx.x < P.total_tiles ? __ldg(P.tile_clip + blockIdx.x) : 0;
+  ClipDesc cd = P.clips[c];
+  for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    // descriptor of this CTA's next tile: fetched now (one tile ahead), used at the bottom of the loop
+    const int nt = tile + gridDim.x;
+    const int c_next = nt < P.total_tiles ? __ldg(P.tile_clip + nt) : c;
+    const ClipDesc cd_next = P.clips[c_next];
+    if (!INIT && warp == 0 && nt < P.total_tiles) {  // pull the accumulator span of the next tile towards L2
+      const float* a = P.acc_in + cd_next.acc_offset + (int64_t)(nt - cd_next.tile_offset) * kWarpsPerCta * P.hop;
+      const int span = (kWarpsPerCta - 1) * P.hop + kNfft;
+      for (int i = lane * 32; i < span; i += 32 * 32) prefetch_l2(a + i);
+    }
+    gl_tile<INIT, FIRST, false>(P, m, c, cd, tile);
     c = c_next;
     cd = cd_next;
+  }
+}
+
+// Small batches (every tile resident at once, e.g. ONE 30 s clip = 162 tiles): all launches of the loop collapse into
+// one cooperative persistent kernel -- tables are staged once, each CTA keeps its tile, iterations are separated by a
+// grid-wide barrier instead of a launch, and the final normalisation runs in the same kernel.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+gl_persistent_kernel(GlParams P, int n_iter, float* acc0, float* acc1, float* acc2, unsigned int* barrier, float* y_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const GlSmem m = gl_smem_setup(smem_raw, P);
+  const int tile = blockIdx.x;  // grid == total_tiles, all co-resident (cooperative launch)
+  const int c = __ldg(P.tile_clip + tile);
+  const ClipDesc cd = P.clips[c];
+  float* acc[3] = {acc0, acc1, acc2};
+  unsigned int target = 0;
+
+  P.acc_in = nullptr; P.acc_out = acc[0]; P.acc_zero = nullptr;
+  gl_tile<true, false, true>(P, m, c, cd, tile);
+  grid_barrier(barrier, target);
+  int cur = 0;
+  for (int j = 1; j <= n_iter; ++j) {
+    P.acc_in = acc[cur];
+    P.acc_out = acc[(cur + 1) % 3];
+    P.acc_zero = acc[(cur + 2) % 3];
+    gl_tile<false, false, true>(P, m, c, cd, tile);  // tprev starts zeroed, so iteration 1 needs no special case
+    grid_barrier(barrier, target);
+    cur = (cur + 1) % 3;
+  }
+  // y[n] = acc[n + 1024] / wss[n + 1024] for this tile's share of the clip
+  {
+    const int t0 = (tile - cd.tile_offset) * kWarpsPerCta;
+    const bool last = t0 + kWarpsPerCta >= cd.frames;
+    const int64_t n0 = (int64_t)t0 * P.hop;
+    const int64_t n1 = last ? cd.length : min((int64_t)(t0 + kWarpsPerCta) * P.hop, cd.length);
+    const float* a = acc[cur] + cd.acc_offset + kHalf;
+    const float* w = P.inv_wss + __ldg(P.wss_off + c) + kHalf;
+    float* dst = y_out + cd.sample_offset;
+    for (int64_t n = n0 + threadIdx.x; n < n1; n += blockDim.x) dst[n] = __ldcg(a + n) * __ldg(w + n);
   }
 }
 
@@ -461,6 +542,34 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
   P.S = S_use; P.tprev = tprev; P.inv_wss = b->d_inv_wss; P.wss_off = b->d_wss_offset;
   P.alpha = momentum / (1.0f + momentum);
   P.init_phase = d_init_phase; P.phase_layout = s_layout; P.init_mode = init_mode; P.seed = seed;
+
+  // Small batch: every tile can be resident at once -> one cooperative persistent kernel for the whole loop.
+  {
+    static int coop_ok[64] = {0};  // 0 unknown, 1 usable, -1 not
+    if (coop_ok[dev] == 0) {
+      int coop = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      if (coop && cudaFuncSetAttribute(gl_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gl_persistent_kernel, kWarpsPerCta * 32, smem) == cudaSuccess &&
+          per_sm >= 2)
+        coop_ok[dev] = 1;
+      else
+        coop_ok[dev] = -1;
+      cudaGetLastError();
+    }
+    if (coop_ok[dev] == 1 && b->total_tiles <= 2 * sms) {
+      unsigned int* barrier = reinterpret_cast<unsigned int*>(ws);  // the 256 spare bytes at the end of the workspace
+      MST_CUDA_OK(cudaMemsetAsync(barrier, 0, 256, s));
+      MST_CUDA_OK(cudaMemsetAsync(tprev, 0, (size_t)b->total_frames * kSpecStride * sizeof(float2), s));
+      P.acc_in = nullptr; P.acc_out = acc[0]; P.acc_zero = nullptr; P.first_iter = 0;
+      int n_it = n_iter;
+      void* args[] = {&P, &n_it, &acc[0], &acc[1], &acc[2], &barrier, &d_y_out};
+      MST_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gl_persistent_kernel), dim3(b->total_tiles),
+                                              dim3(kWarpsPerCta * 32), args, smem, s));
+      count_launch();
+      return MST_OK;
+    }
+  }
 
   // launch 0: y_0 from the initial phase, accumulated into acc[0]
   P.acc_in = nullptr; P.acc_out = acc[0]; P.acc_zero = nullptr; P.first_iter = 1;
