@@ -300,11 +300,12 @@ int mst_pianoroll_rasterize(const int32_t* d_pitch, const int32_t* d_velocity, c
                             const double* d_end, const int64_t* d_note_offsets, int n_pieces,
                             const int64_t* d_row_offsets, int64_t total_rows, int64_t total_notes, int fs,
                             uint8_t* d_roll, int8_t* d_onoff, int32_t* d_velsum, mst_stream_t stream) {
-  if (!d_pitch || !d_velocity || !d_start || !d_end || !d_note_offsets || !d_row_offsets || !d_roll || !d_onoff)
-    return fail(MST_ERR_INVALID, "null argument");
   if (n_pieces <= 0 || fs <= 0 || total_rows < 0 || total_notes < 0) return fail(MST_ERR_INVALID, "bad sizes");
+  if (total_rows == 0) return MST_OK;  // every piece rounds to zero columns: empty rolls, nothing to launch
+  if (!d_note_offsets || !d_row_offsets || !d_roll || !d_onoff ||
+      (total_notes > 0 && (!d_pitch || !d_velocity || !d_start || !d_end)))
+    return fail(MST_ERR_INVALID, "null argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (total_rows == 0) return MST_OK;
   if (reinterpret_cast<uintptr_t>(d_roll) & 15 || reinterpret_cast<uintptr_t>(d_onoff) & 15)
     return fail(MST_ERR_INVALID, "roll / onoff must be 16-byte aligned");
   MST_CUDA_OK(cudaMemsetAsync(d_roll, 0, (size_t)total_rows * 128, s));
@@ -326,9 +327,9 @@ int mst_pianoroll_rasterize(const int32_t* d_pitch, const int32_t* d_velocity, c
 
 int mst_pianoroll_chunks(const void* d_plane, int64_t n_rows, int num_chunks, int chunk_rows, int stride_rows,
                          int out_dtype, void* d_out, mst_stream_t stream) {
-  if (!d_plane || !d_out) return fail(MST_ERR_INVALID, "null argument");
   if (num_chunks < 0 || chunk_rows <= 0 || stride_rows <= 0 || n_rows < 0) return fail(MST_ERR_INVALID, "bad sizes");
-  if (num_chunks == 0) return MST_OK;
+  if (num_chunks == 0) return MST_OK;  // empty result (np.array([]) in the reference): nothing to launch
+  if (!d_out || (!d_plane && n_rows > 0)) return fail(MST_ERR_INVALID, "null argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int64_t total = (int64_t)num_chunks * chunk_rows * 128;
   const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
@@ -347,10 +348,11 @@ int mst_pianoroll_chunks(const void* d_plane, int64_t n_rows, int num_chunks, in
 int mst_pianoroll_upsample(const void* d_plane, const int64_t* d_row_offsets, const int64_t* d_sample_offsets,
                            int n_pieces, int64_t total_samples, int fs, int sr, int pitch_lo, int n_keys, int out_dtype,
                            void* d_out, mst_stream_t stream) {
-  if (!d_plane || !d_row_offsets || !d_sample_offsets || !d_out) return fail(MST_ERR_INVALID, "null argument");
   if (n_pieces <= 0 || fs <= 0 || sr <= 0 || pitch_lo < 0 || n_keys <= 0 || pitch_lo + n_keys > 128)
     return fail(MST_ERR_INVALID, "bad upsample geometry");
   if (total_samples <= 0) return MST_OK;
+  if (!d_row_offsets || !d_sample_offsets || !d_out) return fail(MST_ERR_INVALID, "null argument");
+  // d_plane may be NULL only when every piece has an empty roll (all output samples are then zero)
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int64_t avg = total_samples / n_pieces + 1;
   const int epv = out_dtype == MST_DTYPE_I8 ? 16 : 4;

@@ -50,7 +50,13 @@ class ClipBatch:
         device = _lib.require_cuda(device)
         offsets = torch.as_tensor(np.asarray(offsets, dtype=np.int64))
         lengths = torch.as_tensor(np.asarray(lengths, dtype=np.int64))
-        h = _lib.ops().batch_create(offsets, lengths, n_fft, int(hop), _pad_code(pad_mode), device.index)
+        try:
+            h = _lib.ops().batch_create(offsets, lengths, n_fft, int(hop), _pad_code(pad_mode), device.index)
+        except RuntimeError as e:
+            if "too short" in str(e) or "empty clip" in str(e):
+                # np.pad(mode='reflect') / librosa raise for inputs shorter than the padding: keep the exception type
+                raise ValueError(str(e)) from None
+            raise
         return cls(h, int(offsets.numel()), int(hop), device)
 
     @classmethod
@@ -63,7 +69,12 @@ class ClipBatch:
     def from_frames(cls, frames_per_clip, hop, pad_mode="reflect", device=None, n_fft=N_FFT):
         device = _lib.require_cuda(device)
         frames = torch.as_tensor(np.asarray(frames_per_clip, dtype=np.int64))
-        h = _lib.ops().batch_create_from_frames(frames, n_fft, int(hop), _pad_code(pad_mode), device.index)
+        try:
+            h = _lib.ops().batch_create_from_frames(frames, n_fft, int(hop), _pad_code(pad_mode), device.index)
+        except RuntimeError as e:
+            if "too short" in str(e):
+                raise ValueError(str(e)) from None
+            raise
         return cls(h, int(frames.numel()), int(hop), device)
 
     def clip_frames(self, c):

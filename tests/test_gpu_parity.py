@@ -145,6 +145,33 @@ def test_raw_c_abi_through_ctypes(pkg, gpu):
     lib.mst_batch_destroy(batch)
 
 
+def test_edge_cases_empty_and_short_inputs(pkg, gpu):
+    """Empty / degenerate inputs behave like the reference's NumPy code, or raise the same exception type."""
+    pp = pkg.preprocess
+    y = clip(15, 300000, "noise")
+    out = pp.process_audio_into_chunks(y, "cuba", 1, 0)            # np.array([]) in the reference
+    assert out.shape == (0,)
+    roll = np.zeros((2000, 128)); roll[10:50, 60] = 1
+    a, b = pp.process_pianoroll_into_chunks(roll, roll.copy(), 1, 0)
+    assert a.shape[0] == 0 and b.shape[0] == 0
+    with pytest.raises(ValueError):                                 # np.pad(reflect) on a too-short signal raises too
+        pkg.features.stft(np.zeros(1000, dtype=np.float32), hop_length=256)
+    with pytest.raises(ValueError):
+        pkg.features.griffinlim(np.ones((1025, 2), dtype=np.float32), n_iter=1, hop_length=256)
+    # a piece whose only note rounds to zero columns -> empty roll, and chunking past the end pads with zeros
+    r, o = pp.notes_to_pianoroll([60], [5], [0.0], [0.001])
+    assert r.shape == (0, 128) and o.shape == (0, 128)
+    r, o = pp.notes_to_pianoroll([60, 60], [5, 7], [0.0, 0.1], [1.0, 0.5])   # collision: overlapping same-pitch notes
+    assert r[:, 60].sum() == 172 and o[0, 60] == 1 and o[172 - 1, 60] == 0
+    vs = pkg.pianoroll.get_piano_roll([60, 60], [5, 7], [0.0, 0.1], [1.0, 0.5], 172)
+    assert vs[60, 20] == 12 and vs[60, 10] == 5                     # velocities add where notes overlap
+    # silence in, finite zeros out (log1p(0) = 0; Griffin-Lim of an all-zero spectrogram is silence)
+    z = pp.process_spectrum_from_chunk(np.zeros(8192, dtype=np.float32))
+    assert np.array_equal(z, np.zeros_like(z))
+    w = pkg.features.griffinlim(np.zeros((1025, 20), dtype=np.float32), n_iter=4, hop_length=256)
+    assert np.isfinite(w).all() and np.abs(w).max() == 0.0
+
+
 # ---- P2: mel ----------------------------------------------------------------------------------
 @pytest.mark.parametrize("sr,hop", [(22050, 512), (44100, 256)])
 def test_melspectrogram_and_logmel(pkg, sr, hop):
