@@ -343,100 +343,32 @@ def run_ours(args):
 
 
 def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrier, planes_to_host=False):
-    """Same step through host buffers: pinned host -> device copies and device -> host reads are inside the timing.
+    """Same step through host buffers via the package's public ``pipeline.HostPipeline``: pinned host -> device copies
+    and device -> host reads are inside the timing.
 
     Host inputs: audio, magnitude spectrograms (the model output Griffin-Lim inverts), MIDI note arrays.
     Host outputs: log-mel, reconstructed waveforms, frame-rate piano roll + on/off (what the reference's load_midi
     returns).  The audio-rate int8 planes are the model's conditioning input and stay on the device by default
     (15.5 MB per 4 s clip, 45x the audio itself); `planes_to_host=True` also copies them out (reported separately).
+    Chunks rotate over 4 CUDA streams; measured on B200 at 4096 clips: 1 stream 314 ms, 2: 233 ms, 3: 204 ms,
+    4: 197 ms (kernels alone: 181 ms).
     """
     import torch
+    from ml_music_style_transfer_b200.pipeline import HostPipeline
     n = min(args.clips, args.e2e_clips)
     h_audio = torch.empty(n * CLIP_LEN, dtype=torch.float32).pin_memory()
     h_audio.copy_(audio_d[:n * CLIP_LEN])
     h_S = torch.empty(n * T_FRAMES * K, dtype=torch.float32).pin_memory()
     h_S.copy_(S_d[:n * T_FRAMES * K])
-    h_mel = torch.empty(n * N_MELS * T_FRAMES, dtype=torch.float32).pin_memory()
-    h_y = torch.empty(n * HOP * (T_FRAMES - 1), dtype=torch.float32).pin_memory()
-    sub = max(1, min(n, int(256 * 4.0 / CLIP_SECONDS)))
-    h_planes = torch.empty(2 * sub * N_KEYS * CLIP_LEN, dtype=torch.int8).pin_memory() if planes_to_host else None
-    roll_rows = n * int(ROLL_FS * CLIP_SECONDS)
-    h_roll = torch.empty((roll_rows, 128), dtype=torch.uint8).pin_memory()
-    h_onoff = torch.empty((roll_rows, 128), dtype=torch.int8).pin_memory()
-    no = notes_h[4]
-    n_notes = int(no[n])
-    h_notes = [torch.from_numpy(np.ascontiguousarray(a[:n_notes])).pin_memory() for a in notes_h[:4]]
-    h_noff = torch.from_numpy(np.ascontiguousarray(no[:n + 1])).pin_memory()
-    # The batch is cut into chunks that rotate over a few CUDA streams (4 by default), so that the H2D copies of the next
-    # chunks and the D2H copies of the previous ones overlap the kernels of the current one (the library launches on
-    # torch's current stream).  Measured on B200, 4096 clips: 1 stream 314 ms, 2: 233 ms, 3: 204 ms, 4: 197 ms
-    # (kernels alone: 181 ms).
-    n_chunks = max(1, min(args.e2e_chunks, n // 256)) if n >= 512 else 1
-    bounds = [(n * i) // n_chunks for i in range(n_chunks + 1)]
-    chunks = []
-    rows_per_clip = int(ROLL_FS * CLIP_SECONDS)
-    for ci in range(n_chunks):
-        a0, a1 = bounds[ci], bounds[ci + 1]
-        m = a1 - a0
-        n0, n1 = int(no[a0]), int(no[a1])
-        chunks.append(dict(
-            a0=a0, a1=a1, m=m,
-            batch=F.ClipBatch.uniform(m, CLIP_LEN, HOP, device=device),
-            gl_batch=F.ClipBatch.from_frames([T_FRAMES] * m, HOP, device=device),
-            notes=[t[n0:n1] for t in h_notes],
-            h_max_end=np.array([notes_h[3][no[i]:no[i + 1]].max() for i in range(a0, a1)], dtype=np.float64),
-            noff=torch.from_numpy(np.ascontiguousarray(no[a0:a1 + 1] - no[a0])).pin_memory()))
-    n_streams = max(1, int(os.environ.get("MST_E2E_STREAMS", "4")))
-    streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
-    d2h_roll = [0]
-
-    def step():
-        d2h_roll[0] = 0
-        main = torch.cuda.current_stream()
-        for s_ in streams:
-            s_.wait_stream(main)
-        for ci, ch in enumerate(chunks):
-            a0, a1, m = ch["a0"], ch["a1"], ch["m"]
-            with torch.cuda.stream(streams[ci % n_streams]):
-                a = h_audio[a0 * CLIP_LEN:a1 * CLIP_LEN].to(device, non_blocking=True)
-                mel = F.melspectrogram_batch(a, ch["batch"], plan, log1p=True, layout=F.BIN_MAJOR)
-                h_mel[a0 * N_MELS * T_FRAMES:a1 * N_MELS * T_FRAMES].copy_(mel, non_blocking=True)
-                nb = PR.NoteBatch.__new__(PR.NoteBatch)
-                nb.device = device
-                nb.pitch, nb.velocity, nb.start, nb.end = [t.to(device, non_blocking=True) for t in ch["notes"]]
-                nb.note_offsets = ch["noff"].to(device, non_blocking=True)
-                nb.n_pieces, nb.end_times, nb.pedals, nb.h_max_end = m, None, None, ch["h_max_end"]
-                roll, onoff, row_off, _ = PR.rasterize(nb, ROLL_FS)
-                rows = min(roll.shape[0], m * rows_per_clip)
-                r0 = a0 * rows_per_clip
-                h_roll[r0:r0 + rows].copy_(roll[:rows], non_blocking=True)
-                h_onoff[r0:r0 + rows].copy_(onoff[:rows], non_blocking=True)
-                d2h_roll[0] += 2 * rows * 128
-                for s in range(0, m, sub):
-                    e = min(m, s + sub)
-                    ro = row_off[s:e + 1]
-                    ua, _ = PR.upsample(roll, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
-                    ub, _ = PR.upsample(onoff, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
-                    if planes_to_host:
-                        k = (e - s) * N_KEYS * CLIP_LEN
-                        h_planes[:k].copy_(ua, non_blocking=True)
-                        h_planes[k:2 * k].copy_(ub, non_blocking=True)
-                Sd = h_S[a0 * T_FRAMES * K:a1 * T_FRAMES * K].to(device, non_blocking=True)
-                y = F.griffinlim_batch(Sd, ch["gl_batch"], n_iter=GL_ITERS, momentum=0.99, init="random", seed=7,
-                                       layout=F.FRAME_MAJOR)
-                L = HOP * (T_FRAMES - 1)
-                h_y[a0 * L:a1 * L].copy_(y, non_blocking=True)
-        for s_ in streams:
-            main.wait_stream(s_)
-        torch.cuda.synchronize()
-
-    step()
+    pipe = HostPipeline(n, CLIP_LEN, sr=SR, hop=HOP, n_mels=N_MELS, roll_fs=ROLL_FS, pitch_lo=PITCH_LO, n_keys=N_KEYS,
+                        gl_iters=GL_ITERS, n_chunks=args.e2e_chunks, planes_to_host=planes_to_host, device=device, plan=plan)
+    pipe.run(h_audio, h_S, notes_h)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = max(1, min(args.steps, 3))
     ev0.record()
     for _ in range(reps):
-        step()
+        pipe.run(h_audio, h_S, notes_h)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1) / reps
@@ -445,10 +377,10 @@ def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrie
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    h2d = h_audio.numel() * 4 + h_S.numel() * 4 + sum(t.numel() * t.element_size() for t in h_notes) + h_noff.numel() * 8
-    d2h = h_mel.numel() * 4 + h_y.numel() * 4 + d2h_roll[0] + (2 * n * N_KEYS * CLIP_LEN if planes_to_host else 0)
-    return {"value": world * n * CLIP_SECONDS / (ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "clips_per_gpu": n, "ms_per_step": ms, "pipeline_chunks": n_chunks, "pipeline_streams": n_streams,
+    h2d, d2h = pipe.bytes_per_run()
+    return {"value": world * n * CLIP_SECONDS / (ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "clips_per_gpu": n, "ms_per_step": ms, "pipeline_chunks": len(pipe.chunks),
+            "pipeline_streams": pipe.n_streams, "api": "ml_music_style_transfer_b200.pipeline.HostPipeline.run",
             "outputs_to_host": "log-mel, waveforms, frame-rate roll+onoff" + (", audio-rate planes" if planes_to_host else
                                " (audio-rate planes stay on the device for the model)")}
 

@@ -530,3 +530,45 @@ def test_full_size_properties(pkg, gpu):
     y = F.griffinlim_batch(D.abs().contiguous(), gb, n_iter=2, init_phase=ph, layout=F.FRAME_MAJOR).view(nb, -1)
     ref = audio.view(n, -1)[:nb, :y.shape[1]]
     assert (y - ref)[:, 2048:-2048].abs().max() < 2e-3
+
+
+def test_host_pipeline_matches_direct_calls(pkg, gpu):
+    """pipeline.HostPipeline (chunks over several streams, pinned host buffers) == the direct batched ops."""
+    import bench
+    from ml_music_style_transfer_b200.pipeline import HostPipeline
+    F, PR = pkg.features, pkg.pianoroll
+    n, clip_len = 600, 22050  # 1 s clips -> two chunks
+    audio = bench.make_audio_device(152, gpu, 9)[:n * clip_len].contiguous()
+    batch = F.ClipBatch.uniform(n, clip_len, 512, device=gpu)
+    T = batch.total_frames // n
+    S = F.stft_batch(audio, batch, "magnitude", F.FRAME_MAJOR)
+    from ml_music_style_transfer_b200 import synth
+    pieces = [synth.midi_piece(i, seconds=1.0) for i in range(n)]
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(p[0]) for p in pieces], out=offs[1:])
+    notes = tuple(np.concatenate([p[j] for p in pieces]) for j in range(4)) + (offs,)
+    h_audio, h_S = audio.cpu().pin_memory(), S.cpu().pin_memory()
+    pipe = HostPipeline(n, clip_len, n_chunks=4, n_streams=3, planes_to_host=False, device=gpu)
+    assert len(pipe.chunks) == 2
+    pipe.run(h_audio, h_S, notes)
+    plan = F.MelPlan.get(22050, device=gpu)
+    mel = F.melspectrogram_batch(audio, batch, plan, log1p=True, layout=F.BIN_MAJOR).cpu()
+    assert torch.equal(pipe.h_mel, mel)
+    nb = PR.NoteBatch(*notes, device=gpu)
+    roll, onoff, row_off, _ = PR.rasterize(nb, 250)
+    ro = row_off.cpu().numpy()
+    for i in (0, 299, 300, 599):  # both sides of the chunk boundary
+        r = min(int(ro[i + 1] - ro[i]), pipe.rows_per_clip)
+        # the pipeline packs each chunk's rows back to back starting at chunk_start * rows_per_clip
+        c0 = 0 if i < 300 else 300
+        base = c0 * pipe.rows_per_clip + int(ro[i] - ro[c0])
+        assert torch.equal(pipe.h_roll[base:base + r], roll[ro[i]:ro[i] + r].cpu())
+        assert torch.equal(pipe.h_onoff[base:base + r], onoff[ro[i]:ro[i] + r].cpu())
+    # Griffin-Lim: the random phase stream differs per chunk, so compare convergence, clip by clip
+    L = 512 * (T - 1)
+    for i in (0, 450):
+        w = pipe.h_wave[i * L:(i + 1) * L].numpy()
+        Si = S.view(n, T, 1025)[i].t().cpu().numpy()
+        assert ogl.spectral_convergence(Si, w, 512) < 0.6
+    h2d, d2h = pipe.bytes_per_run()
+    assert h2d > h_audio.numel() * 4 and d2h > pipe.h_mel.numel() * 4
