@@ -292,7 +292,10 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, pkg, F, PR, device, audio, S, notes_h, plan, world, barrier)
-        e2e_all = run_e2e(args, pkg, F, PR, device, audio, S, notes_h, plan, world, barrier, planes_to_host=True)
+        try:   # the 15 MB-per-clip variant is informative only: never let it take the main line down
+            e2e_all = run_e2e(args, pkg, F, PR, device, audio, S, notes_h, plan, world, barrier, planes_to_host=True)
+        except Exception as exc:  # noqa: BLE001
+            e2e_all = {"error": repr(exc)}
 
     if rank == 0:
         props = torch.cuda.get_device_properties(device)
