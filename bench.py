@@ -252,6 +252,26 @@ def run_ours(args):
         total_audio = float(ta_.item())
     value = total_audio / (ms_per_step * 1e-3)
 
+    # ---- optional final gather of the features over NCCL (north_star: "NCCL over NVLink used only for the optional
+    # final gather"); measured separately, never part of `value` -------------------------------------------------------
+    gather = None
+    if args.gather and world > 1:
+        from ml_music_style_transfer_b200 import sharding
+        feats = stage_a().view(n_clips, N_MELS * T_FRAMES)
+        sharding.gather_features(feats, n_clips * world)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = sharding.gather_features(feats, n_clips * world)
+        g1.record()
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1)], device=device, dtype=torch.float64)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        ok = bool(torch.equal(full[rank * n_clips:(rank + 1) * n_clips], feats))
+        gather = {"ms": float(gms.item()), "bytes_received_per_rank": int(full.numel() * 4), "own_shard_intact": ok,
+                  "algbw_gbs": full.numel() * 4 / (float(gms.item()) * 1e-3) / 1e9}
+        del full, feats
+
     # ---- configs[0]/[1] of BASELINE.json: ONE 30 s clip (latency view; tiny against a B200, reported for completeness) ----
     single = None
     if rank == 0 and not args.no_single:
@@ -340,6 +360,8 @@ def run_ours(args):
         if not args.no_single:
             line["single_clip_30s"] = single
             line["extras"] = extras
+        if gather is not None:
+            line["final_gather_logmel"] = gather
         if e2e is not None:
             line["e2e"] = e2e
             line["e2e_planes_to_host"] = e2e_all
@@ -471,6 +493,7 @@ def main():
                          "in total, sharded over the ranks (strong scaling)")
     ap.add_argument("--clips", type=int, default=None, help="clips per GPU (default: 16384 for c4, 4080/world for c5)")
     ap.add_argument("--gl-sub", type=int, default=16384, help="clips per Griffin-Lim call (workspace bound)")
+    ap.add_argument("--gather", action="store_true", help="also time the optional NCCL all-gather of the log-mel features")
     ap.add_argument("--no-single", action="store_true", help="skip the single 30 s clip latency section")
     ap.add_argument("--e2e-clips", type=int, default=4096, help="clips per GPU for the host-buffer end-to-end pass")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline depth of the end-to-end pass (chunks rotating over MST_E2E_STREAMS streams, default 4)")
