@@ -425,6 +425,23 @@ def test_griffinlim_ragged_batch_matches_per_clip_oracle(pkg, gpu):
     assert o == out.shape[0]
 
 
+@pytest.mark.parametrize("hop", [128, 300, 441, 1024])
+def test_other_hops(pkg, hop):
+    """Hops the reference never uses still follow librosa: odd hops take the unaligned frame loader, hop 128 / 1024 the
+    R = 16 / R = 2 overlap-add, non-power-of-two hops the generic overlap-add and the per-frame envelope path."""
+    y = clip(36, 20000 + hop)
+    ref = ostft.stft(y, 2048, hop)
+    got = pkg.features.stft(y, hop_length=hop)
+    assert_close(got, ref)
+    S = np.abs(ref).astype(np.float32)
+    u = ogl.random_phase(S.shape, 2)
+    for n_iter in (0, 3):
+        w_ref = ogl.griffinlim(S, n_iter, hop, init_phase=u)
+        w_got = pkg.features.griffinlim(S, n_iter=n_iter, hop_length=hop, init_phase=u)
+        assert w_got.shape == w_ref.shape
+        assert rel_l2(w_got, w_ref.astype(np.float64)) < 5e-4, (hop, n_iter, rel_l2(w_got, w_ref.astype(np.float64)))
+
+
 def test_griffinlim_early_iterations_match_waveform(pkg):
     """Before the chaotic phase dynamics amplify float32 rounding, the waveform itself must agree."""
     y = clip(32, 30000)
