@@ -210,6 +210,7 @@ static int launch_stft(const float* d_audio, const mst_batch* b, int layout, voi
   static bool attr_set[64] = {false};
   int dev = 0;
   MST_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(MST_ERR_INVALID, "device index %d out of range", dev);
   if (!attr_set[dev]) {
     MST_CUDA_OK(cudaFuncSetAttribute(stft_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[dev] = true;

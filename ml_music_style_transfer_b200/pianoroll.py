@@ -39,6 +39,20 @@ class NoteBatch:
         self.pedals = pedals
 
     @classmethod
+    def from_host_tensors(cls, pitch, velocity, start, end, note_offsets, h_max_end, device=None):
+        """Asynchronous construction from (pinned) host tensors on the current stream; ``h_max_end`` is the latest note
+        end of every piece (host float64 array), which spares rasterize() a device read-back."""
+        self = cls.__new__(cls)
+        self.device = _lib.require_cuda(device)
+        self.pitch, self.velocity, self.start, self.end = [t.to(self.device, non_blocking=True)
+                                                           for t in (pitch, velocity, start, end)]
+        self.note_offsets = note_offsets.to(self.device, non_blocking=True)
+        self.n_pieces = int(note_offsets.numel()) - 1
+        self.end_times, self.pedals = None, None
+        self.h_max_end = np.asarray(h_max_end, dtype=np.float64)
+        return self
+
+    @classmethod
     def from_pieces(cls, pieces, device=None):
         """pieces: iterable of (pitch, velocity, start, end) array tuples."""
         ps, vs, ss, es, offs = [], [], [], [], [0]

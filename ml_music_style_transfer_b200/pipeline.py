@@ -87,11 +87,7 @@ class HostPipeline:
                 a = h_audio[a0 * self.clip_len:a1 * self.clip_len].to(dev, non_blocking=True)
                 mel = F.melspectrogram_batch(a, ch["batch"], self.plan, log1p=True, layout=F.BIN_MAJOR)
                 self.h_mel[a0 * self.n_mels * self.frames:a1 * self.n_mels * self.frames].copy_(mel, non_blocking=True)
-                nb = PR.NoteBatch.__new__(PR.NoteBatch)
-                nb.device = dev
-                nb.pitch, nb.velocity, nb.start, nb.end = [t.to(dev, non_blocking=True) for t in ch["notes"]]
-                nb.note_offsets = ch["noff"].to(dev, non_blocking=True)
-                nb.n_pieces, nb.end_times, nb.pedals, nb.h_max_end = m, None, None, ch["h_max_end"]
+                nb = PR.NoteBatch.from_host_tensors(*ch["notes"], ch["noff"], ch["h_max_end"], device=dev)
                 roll, onoff, row_off, _ = PR.rasterize(nb, self.roll_fs)
                 rows = min(roll.shape[0], m * self.rows_per_clip)
                 r0 = a0 * self.rows_per_clip
