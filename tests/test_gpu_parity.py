@@ -442,6 +442,40 @@ def test_other_hops(pkg, hop):
         assert rel_l2(w_got, w_ref.astype(np.float64)) < 5e-4, (hop, n_iter, rel_l2(w_got, w_ref.astype(np.float64)))
 
 
+@pytest.mark.parametrize("hop", [128, 256, 512, 1024])
+def test_griffinlim_all_tile_remainders(pkg, gpu, hop):
+    """Every frame count from the shortest legal clip up to 3+ tiles in ONE ragged batch: exercises first / last / only
+    tile flags, partial tiles, clips with no interior frame, and the shared / exclusive overlap-add blocks."""
+    F = pkg.features
+    t_min = 1024 // hop + 2                      # hop * (T - 1) must exceed n_fft / 2 (reflect padding)
+    frames = list(range(t_min, t_min + 27))
+    rng = np.random.default_rng(hop)
+    S_list = [np.abs(rng.standard_normal((1025, T))).astype(np.float32) for T in frames]
+    u_list = [rng.random((1025, T)).astype(np.float32) for T in frames]
+    gb = F.ClipBatch.from_frames(frames, hop, device=gpu)
+    S = torch.from_numpy(np.concatenate([s.ravel() for s in S_list])).to(gpu)
+    ph = torch.from_numpy(np.concatenate([u.ravel() for u in u_list])).to(gpu)
+    for n_iter in (0, 2):
+        out = F.griffinlim_batch(S, gb, n_iter=n_iter, init_phase=ph, layout=F.BIN_MAJOR).cpu().numpy()
+        o = 0
+        for Sm, u, T in zip(S_list, u_list, frames):
+            L = hop * (T - 1)
+            ref = ogl.griffinlim(Sm, n_iter, hop, init_phase=u)
+            err = rel_l2(out[o:o + L], ref.astype(np.float64))
+            assert err < 5e-4, (hop, T, n_iter, err)
+            o += L
+        assert o == out.shape[0]
+    # the same clips replicated past 2 x n_SM tiles take the multi-launch path (one kernel per iteration) instead of the
+    # cooperative persistent kernel: both must give the same waveforms, replica after replica
+    reps = 14
+    gb2 = F.ClipBatch.from_frames(frames * reps, hop, device=gpu)
+    out2 = F.griffinlim_batch(S.repeat(reps), gb2, n_iter=2, init_phase=ph.repeat(reps), layout=F.BIN_MAJOR).cpu().numpy()
+    assert out2.shape[0] == reps * out.shape[0]
+    for r in (0, reps // 2, reps - 1):
+        seg = out2[r * out.shape[0]:(r + 1) * out.shape[0]]
+        assert rel_l2(seg, out.astype(np.float64)) < 1e-5, (hop, r)
+
+
 def test_griffinlim_early_iterations_match_waveform(pkg):
     """Before the chaotic phase dynamics amplify float32 rounding, the waveform itself must agree."""
     y = clip(32, 30000)
