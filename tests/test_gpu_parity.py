@@ -172,6 +172,30 @@ def test_edge_cases_empty_and_short_inputs(pkg, gpu):
     assert np.isfinite(w).all() and np.abs(w).max() == 0.0
 
 
+@pytest.mark.parametrize("hop,pad", [(256, "reflect"), (512, "constant")])
+def test_stft_all_tile_remainders(pkg, gpu, hop, pad):
+    """Ragged batch whose clips cover every frame count mod 8 (partial tiles) and odd sample offsets (unaligned
+    loads), in both output layouts."""
+    F = pkg.features
+    lens = [1025 + 37 * i + hop * (i % 11) for i in range(30)]
+    offs = np.concatenate([[0], np.cumsum([l + (i % 3) for i, l in enumerate(lens)])[:-1]])  # some odd offsets
+    y = clip(16, int(offs[-1] + lens[-1] + 8), "noise")
+    a = torch.from_numpy(y).to(gpu)
+    b = F.ClipBatch.from_clips(offs, lens, hop, pad_mode=pad, device=gpu)
+    fm = F.stft_batch(a, b, "complex").cpu().numpy()
+    bm = F.stft_batch(a, b, "log1p_power", F.BIN_MAJOR).cpu().numpy()
+    f0 = 0
+    seen = set()
+    for o, l in zip(offs, lens):
+        ref = ostft.stft(y[o:o + l], 2048, hop, pad_mode=pad, out_dtype=np.complex128)
+        T = ref.shape[1]
+        seen.add(T % 8)
+        assert_close(fm[f0:f0 + T].T, ref)
+        assert_close(bm[f0 * 1025:(f0 + T) * 1025].reshape(1025, T), np.log1p(np.abs(ref) ** 2))
+        f0 += T
+    assert f0 == b.total_frames and len(seen) >= 6
+
+
 # ---- P2: mel ----------------------------------------------------------------------------------
 @pytest.mark.parametrize("sr,hop", [(22050, 512), (44100, 256)])
 def test_melspectrogram_and_logmel(pkg, sr, hop):
