@@ -124,6 +124,18 @@ def mel_filterbank(sr, n_fft=N_FFT, n_mels=128, fmin=0.0, fmax=None):
     return _lib.ops().mel_filterbank(int(sr), int(n_fft), int(n_mels), float(fmin), 0.0 if fmax is None else float(fmax))
 
 
+def to_numpy(t):
+    """Device tensor -> NumPy.  Large results go through page-locked memory from torch's caching host allocator (one DMA,
+    no pageable staging): the returned array aliases that pinned block, which returns to the cache when the array dies."""
+    t = t.contiguous()
+    if t.numel() * t.element_size() < (1 << 20):
+        return t.cpu().numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
+
+
 def _to_device_audio(y, device=None):
     """Returns (float32 CUDA 1-D tensor, was_numpy)."""
     if isinstance(y, torch.Tensor):
@@ -153,16 +165,16 @@ def stft(y, n_fft=N_FFT, hop_length=None, win_length=None, window="hann", center
     hop = n_fft // 4 if hop_length is None else int(hop_length)
     a, was_np = _to_device_audio(y)
     with ClipBatch.uniform(1, a.numel(), hop, pad_mode=pad_mode, device=a.device) as b:
-        out = stft_batch(a, b, "complex").t()  # (1025, T) view over [T][1025] memory == Fortran order
-    return out.cpu().numpy() if was_np else out
+        out = stft_batch(a, b, "complex")  # [T][1025] memory; its transpose view == librosa's Fortran-ordered (1025, T)
+    return to_numpy(out).T if was_np else out.t()
 
 
 def spectrogram(y, hop_length, out="log1p_power", pad_mode="reflect"):
     """(1025, T) float32 epilogue of the STFT for one clip (Fortran-ordered view)."""
     a, was_np = _to_device_audio(y)
     with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device) as b:
-        o = stft_batch(a, b, out).view(b.total_frames, N_BINS).t()
-    return o.cpu().numpy() if was_np else o
+        o = stft_batch(a, b, out).view(b.total_frames, N_BINS)
+    return to_numpy(o).T if was_np else o.t()
 
 
 def melspectrogram(y=None, sr=22050, n_fft=N_FFT, hop_length=512, n_mels=128, fmin=0.0, fmax=None, pad_mode="reflect",
@@ -173,7 +185,7 @@ def melspectrogram(y=None, sr=22050, n_fft=N_FFT, hop_length=512, n_mels=128, fm
     plan = MelPlan.get(sr, n_fft, n_mels, fmin, fmax, a.device)
     with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device) as b:
         o = melspectrogram_batch(a, b, plan, log1p=log1p, layout=BIN_MAJOR).view(n_mels, b.total_frames)
-    return o.cpu().numpy() if was_np else o
+    return to_numpy(o) if was_np else o
 
 
 def logmel(y, sr=22050, n_fft=N_FFT, hop_length=512, n_mels=128, **kw):
@@ -223,7 +235,7 @@ def griffinlim(S, n_iter=32, hop_length=None, win_length=None, window="hann", mo
     seed = int(np.random.randint(0, 2 ** 31 - 1))
     with ClipBatch.from_frames([T], hop, pad_mode=pad_mode, device=device) as b:
         y = griffinlim_batch(S_flat.to(torch.float32), b, n_iter, momentum, ph, init, seed, layout)
-    return y.cpu().numpy() if was_np else y
+    return to_numpy(y) if was_np else y
 
 
 def spectral_convergence(S, y, hop_length, pad_mode="reflect"):

@@ -65,4 +65,4 @@ class AudioSynthesizer():
         with features.ClipBatch.from_frames([T], int(hop_length), device=device) as b:
             y = features.griffinlim_batch(S.contiguous(), b, n_iter=n_iter, momentum=0.99, init_phase=ph, init="random",
                                           seed=seed, layout=features.BIN_MAJOR, is_log1p_power=True)
-        return y.cpu().numpy() if was_np else y
+        return features.to_numpy(y) if was_np else y

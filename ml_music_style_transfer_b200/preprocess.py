@@ -64,7 +64,7 @@ def process_audio_into_chunks(audio, style, song_id, num_chunks, debug=False):
     with features.ClipBatch.uniform(num_chunks, n_samples_per_chunk, hp.ws, clip_stride=step, device=a.device) as b:
         T = b.total_frames // num_chunks
         out = features.stft_batch(a, b, "log1p_power", features.BIN_MAJOR).view(num_chunks, features.N_BINS, T)
-    return out.cpu().numpy() if was_np else out
+    return features.to_numpy(out) if was_np else out
 
 
 def process_pianoroll_into_chunks(pianoroll, onoff, song_id, num_chunks, debug=False):
@@ -84,7 +84,7 @@ def process_pianoroll_into_chunks(pianoroll, onoff, song_id, num_chunks, debug=F
     score = _pr.chunks(dev(pianoroll), num_chunks, n_windows_per_chunk, hp.stride, out_dtype)
     oo = _pr.chunks(dev(onoff), num_chunks, n_windows_per_chunk, hp.stride, out_dtype)
     if was_np:
-        return score.cpu().numpy(), oo.cpu().numpy()
+        return features.to_numpy(score), features.to_numpy(oo)
     return score, oo
 
 
