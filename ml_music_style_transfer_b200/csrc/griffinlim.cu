@@ -11,9 +11,15 @@
 // rotating overlap-add accumulators (read y_{j-1}, accumulate y_j, zero the one the next launch accumulates into).
 // The phase itself never touches HBM: it is recomputed from rebuilt_j and rebuilt_{j-1} in registers.
 //
-// Overlap-add: the 8 frames of a tile are summed in shared memory in frame order, the tile's span is then added to
-// the global accumulator with float atomics.  With hop >= 256 at most two tiles touch any sample and the buffer starts
-// at zero, so the result does not depend on the order the two adds land in (a + b == b + a): runs are reproducible.
+// Overlap-add: the 8 frames of a tile are summed in shared memory in frame order, hop-block by hop-block.  Blocks that
+// only this tile touches are written with plain 128-bit stores; the blocks a tile shares with its neighbour go to the
+// global accumulator as 128-bit vector reductions (red.global.add.v4.f32).  At most two tiles touch a shared sample
+// (hop >= 256) and the shared region was zeroed one launch earlier, so the result does not depend on the order the two
+// adds land in (a + b == b + a): runs are reproducible.
+//
+// Large batches: one launch per iteration (persistent CTAs walk the tiles).  Small batches (every tile resident at once,
+// e.g. a single clip): gl_persistent_kernel runs the whole loop in ONE cooperative launch with a grid-wide barrier
+// between iterations.
 #include <algorithm>
 #include "fft_warp.cuh"
 #include "mst_common.cuh"
