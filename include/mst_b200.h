@@ -166,6 +166,13 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
                        int n_iter, float momentum, const float* d_init_phase, int init_mode, uint64_t seed,
                        float* d_y_out, void* d_workspace, size_t workspace_bytes, mst_stream_t stream);
 
+/* Spectral convergence of waveforms against target magnitudes, the normalised form of the Frobenius loss the
+ * reference prints at model/inference.py:149-150: per clip c, d_num[c] = sum (|STFT(y_c)| - S_c)^2 and
+ * d_den[c] = sum S_c^2 (double; SC_c = sqrt(num/den)).  `batch` describes the clips of d_y (mst_batch_create);
+ * d_S holds one (1025 x T_c) block per clip in `s_layout`.  Fused into the STFT kernel: no spectrogram is written. */
+int mst_spectral_convergence_f32(const float* d_y, const mst_batch_t* batch, const float* d_S, int s_layout,
+                                 double* d_num, double* d_den, mst_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * "Next" row: the resampling half of librosa.load(path, sr=hp.sr)
  * [preprocess.py:106, model/inference.py:54, tests/test_griffinlim.py:16] = resampy 'kaiser_best'

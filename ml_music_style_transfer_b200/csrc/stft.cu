@@ -13,6 +13,7 @@
 
 namespace mst {
 
+constexpr int kModeConv = 5;          // internal epilogue: per-clip sums of (|S| - S_target)^2 and S_target^2 (spectral convergence)
 constexpr int kModeSplit = 4;         // internal epilogue: |S|^2 as split bf16 (hi, lo) rows for the tensor-core mel projection
 constexpr int kTileStride = 1028;     // floats per frame row of the bin-major staging tile (== 4 mod 32: conflict-free)
 
@@ -20,6 +21,10 @@ struct SplitOut {          // ring of split-precision power-spectrum rows (kSpec
   __nv_bfloat16* hi;
   __nv_bfloat16* lo;
   int64_t g0;              // global frame id stored in ring row 0
+  // kModeConv only: target magnitudes (layout `layout`) and per-clip accumulators
+  const float* target;
+  double* num;             // [n_clips] sum (|STFT(y)| - S)^2
+  double* den;             // [n_clips] sum S^2
 };
 
 // Load one frame (centre-padded, reflect or zero) as z[m] = x[2m] + i*x[2m+1], m = 32*r + lane, times the window.
@@ -117,6 +122,35 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
       rfft2048_warp(v, o, &mid, scratch, s_tw1024, s_twp, lane);
     }
     const int64_t g = cd.frame_offset + t;  // global frame id
+
+    if (MODE == kModeConv) {
+      // spectral convergence: || |STFT(y)| - S ||_F^2 and || S ||_F^2 per clip (model/inference.py:149-150, normalised)
+      double num = 0.0, den = 0.0;
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 33; ++j) {
+          if (j == 32 && lane != 0) break;
+          const int k = j < 32 ? mirror_bin(lane, kb, j) : 512;
+          const float2 xv = j < 32 ? o[j] : mid;
+          const float mag = sqrtf(fmaf(xv.x, xv.x, xv.y * xv.y));
+          const int64_t idx = layout == MST_LAYOUT_FRAME_MAJOR ? g * kBins + k
+                                                                : cd.frame_offset * kBins + (int64_t)k * cd.frames + t;
+          const float sref = __ldg(split.target + idx);
+          const float d = mag - sref;
+          num += (double)d * (double)d;
+          den += (double)sref * (double)sref;
+        }
+      }
+      for (int off = 16; off; off >>= 1) {
+        num += __shfl_xor_sync(MST_FULL_MASK, num, off);
+        den += __shfl_xor_sync(MST_FULL_MASK, den, off);
+      }
+      if (active && lane == 0) {
+        atomicAdd(split.num + c, num);
+        atomicAdd(split.den + c, den);
+      }
+      continue;
+    }
 
     if (MODE == MST_OUT_COMPLEX) {
       if (active) {
@@ -248,6 +282,20 @@ int mst_stft_f32(const float* d_audio, const mst_batch_t* b, int out_mode, int l
     case MST_OUT_LOG1P_POWER: return launch_stft<MST_OUT_LOG1P_POWER>(d_audio, b, layout, d_out, none, 0, nt, s);
     default: return fail(MST_ERR_INVALID, "bad out_mode %d", out_mode);
   }
+}
+
+int mst_spectral_convergence_f32(const float* d_y, const mst_batch_t* b, const float* d_S, int s_layout, double* d_num,
+                                 double* d_den, mst_stream_t stream) {
+  if (!d_y || !b || !d_S || !d_num || !d_den) return fail(MST_ERR_INVALID, "mst_spectral_convergence_f32: null argument");
+  if (s_layout != MST_LAYOUT_FRAME_MAJOR && s_layout != MST_LAYOUT_BIN_MAJOR) return fail(MST_ERR_INVALID, "bad layout %d", s_layout);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  MST_CUDA_OK(cudaMemsetAsync(d_num, 0, sizeof(double) * (size_t)b->n_clips, s));
+  MST_CUDA_OK(cudaMemsetAsync(d_den, 0, sizeof(double) * (size_t)b->n_clips, s));
+  SplitOut so{};
+  so.target = d_S;
+  so.num = d_num;
+  so.den = d_den;
+  return launch_stft<kModeConv>(d_y, b, s_layout, nullptr, so, 0, b->total_tiles, s);
 }
 
 int mst_mel_plan_create(const float* W, int n_mels, int n_bins, mst_mel_plan_t** out) {

@@ -197,6 +197,19 @@ at::Tensor griffinlim(const at::Tensor& S, int64_t s_layout, bool s_is_log1p_pow
   return y;
 }
 
+at::Tensor spectral_convergence(const at::Tensor& y, int64_t batch, const at::Tensor& S, int64_t s_layout) {
+  want(y, at::kFloat, "y");
+  want(S, at::kFloat, "S");
+  c10::cuda::CUDAGuard guard(y.device());
+  mst_batch_t* b = as_batch(batch);
+  TORCH_CHECK(S.numel() == mst_batch_total_frames(b) * 1025, "S does not match the batch");
+  const int64_t n = mst_batch_n_clips(b);
+  at::Tensor sums = at::empty({2, n}, y.options().dtype(at::kDouble));
+  check(mst_spectral_convergence_f32(y.data_ptr<float>(), b, S.data_ptr<float>(), (int)s_layout, sums.data_ptr<double>(),
+                                     sums.data_ptr<double>() + n, cur_stream()), "mst_spectral_convergence_f32");
+  return at::sqrt(sums[0] / sums[1]);
+}
+
 at::Tensor resample(const at::Tensor& x, int64_t sr_in, int64_t sr_out) {
   want(x, at::kFloat, "x");
   TORCH_CHECK(x.dim() == 1, "resample expects a 1-D mono signal");
@@ -234,6 +247,7 @@ TORCH_LIBRARY(mst_b200, m) {
   m.def("pianoroll_upsample(Tensor plane, Tensor row_offsets, Tensor sample_offsets, int total_samples, int fs, int sr, "
         "int pitch_lo, int n_keys, int out_dtype) -> Tensor");
   m.def("resample(Tensor x, int sr_in, int sr_out) -> Tensor");
+  m.def("spectral_convergence(Tensor y, int batch, Tensor S, int s_layout) -> Tensor");
   m.def("griffinlim(Tensor S, int s_layout, bool s_is_log1p_power, int batch, int n_iter, float momentum, "
         "Tensor? init_phase, int init_mode, int seed) -> Tensor");
 }
@@ -247,4 +261,5 @@ TORCH_LIBRARY_IMPL(mst_b200, CUDA, m) {
   m.impl("pianoroll_upsample", &pianoroll_upsample);
   m.impl("griffinlim", &griffinlim);
   m.impl("resample", &resample);
+  m.impl("spectral_convergence", &spectral_convergence);
 }

@@ -238,10 +238,19 @@ def griffinlim(S, n_iter=32, hop_length=None, win_length=None, window="hann", mo
     return to_numpy(y) if was_np else y
 
 
+def spectral_convergence_batch(y, batch, S, layout=BIN_MAJOR):
+    """Per-clip || |STFT(y_c)| - S_c ||_F / || S_c ||_F, fused into the STFT kernel (no spectrogram is materialised).
+    ``batch`` describes the clips of the waveform buffer ``y``; ``S`` holds one (1025 x T_c) block per clip in ``layout``."""
+    return _lib.ops().spectral_convergence(y.contiguous().view(-1), batch.handle, S.contiguous().view(-1), layout)
+
+
 def spectral_convergence(S, y, hop_length, pad_mode="reflect"):
-    """|| |STFT(y)| - S ||_F / ||S||_F on the device (normalised form of model/inference.py:149-150)."""
+    """|| |STFT(y)| - S ||_F / ||S||_F for one clip (normalised form of the loss printed at model/inference.py:149-150)."""
     a, _ = _to_device_audio(y)
     if not isinstance(S, torch.Tensor):
         S = torch.from_numpy(np.ascontiguousarray(S, dtype=np.float32)).to(a.device)
-    R = spectrogram(a, hop_length, out="magnitude", pad_mode=pad_mode)
-    return float(torch.linalg.norm(R.double() - S.double()) / torch.linalg.norm(S.double()))
+    with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device) as b:
+        if S.shape != (N_BINS, b.total_frames):
+            raise ValueError(f"S must be (1025, {b.total_frames}) for this waveform; got {tuple(S.shape)}")
+        sc = spectral_convergence_batch(a, b, S.to(torch.float32), BIN_MAJOR)
+    return float(sc[0])

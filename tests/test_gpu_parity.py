@@ -500,6 +500,28 @@ def test_griffinlim_all_tile_remainders(pkg, gpu, hop):
         assert rel_l2(seg, out.astype(np.float64)) < 1e-5, (hop, r)
 
 
+def test_spectral_convergence_fused(pkg, gpu):
+    """mst_spectral_convergence_f32 (fused STFT epilogue + per-clip reduction) == the oracle's Frobenius ratio."""
+    F = pkg.features
+    frames, hop = [60, 173, 45], 512
+    ys, Ss = [], []
+    for i, T in enumerate(frames):
+        yy = clip(70 + i, hop * (T - 1))
+        S = np.abs(ostft.stft(clip(80 + i, hop * (T - 1), "noise"), 2048, hop)).astype(np.float32)  # unrelated target
+        ys.append(yy); Ss.append(S)
+    y = torch.from_numpy(np.concatenate(ys)).to(gpu)
+    lens = [len(v) for v in ys]
+    b = F.ClipBatch.from_clips(np.concatenate([[0], np.cumsum(lens)[:-1]]), lens, hop, device=gpu)
+    S_bm = torch.from_numpy(np.concatenate([S.ravel() for S in Ss])).to(gpu)
+    S_fm = torch.from_numpy(np.concatenate([S.T.ravel() for S in Ss])).to(gpu)
+    got_bm = F.spectral_convergence_batch(y, b, S_bm, F.BIN_MAJOR).cpu().numpy()
+    got_fm = F.spectral_convergence_batch(y, b, S_fm, F.FRAME_MAJOR).cpu().numpy()
+    for i in range(3):
+        ref = ogl.spectral_convergence(Ss[i], ys[i], hop)
+        assert abs(got_bm[i] - ref) < 1e-5 * ref and abs(got_fm[i] - ref) < 1e-5 * ref
+    assert abs(F.spectral_convergence(Ss[1], ys[1], hop) - ogl.spectral_convergence(Ss[1], ys[1], hop)) < 1e-5
+
+
 def test_griffinlim_early_iterations_match_waveform(pkg):
     """Before the chaotic phase dynamics amplify float32 rounding, the waveform itself must agree."""
     y = clip(32, 30000)
