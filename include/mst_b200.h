@@ -161,7 +161,9 @@ int mst_pianoroll_upsample(const void* d_plane, const int64_t* d_row_offsets, co
  * d_y_out: packed waveforms, clip c at sample offset sum_{j<c} hop*(T_j-1).
  * State (previous iterate, overlap-add accumulators) lives in the caller's workspace in HBM.
  * ------------------------------------------------------------------------------------------- */
-size_t mst_griffinlim_workspace_bytes(const mst_batch_t* batch);
+size_t mst_griffinlim_workspace_bytes(const mst_batch_t* batch); /* worst case over layouts */
+/* Exact size for a given input form: frame-major magnitudes are used in place (no 4 B/bin copy: 16 B/bin of state). */
+size_t mst_griffinlim_workspace_bytes_ex(const mst_batch_t* batch, int s_layout, int s_is_log1p_power);
 int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, const mst_batch_t* batch,
                        int n_iter, float momentum, const float* d_init_phase, int init_mode, uint64_t seed,
                        float* d_y_out, void* d_workspace, size_t workspace_bytes, mst_stream_t stream);

@@ -475,11 +475,17 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 extern "C" {
 
-size_t mst_griffinlim_workspace_bytes(const mst_batch_t* b) {
+size_t mst_griffinlim_workspace_bytes_ex(const mst_batch_t* b, int s_layout, int s_is_log1p_power) {
   if (!b) return 0;
   const size_t spec = (size_t)b->total_frames * kBins;
-  return align_up((size_t)b->total_frames * kSpecStride * sizeof(float2), 256) + align_up(spec * sizeof(float), 256) +
+  const bool needs_copy = s_layout != MST_LAYOUT_FRAME_MAJOR || s_is_log1p_power;  // else the caller's S is used in place
+  return align_up((size_t)b->total_frames * kSpecStride * sizeof(float2), 256) +
+         (needs_copy ? align_up(spec * sizeof(float), 256) : 0) +
          3 * align_up((size_t)b->total_acc * sizeof(float), 256) + 256;
+}
+
+size_t mst_griffinlim_workspace_bytes(const mst_batch_t* b) {
+  return mst_griffinlim_workspace_bytes_ex(b, MST_LAYOUT_BIN_MAJOR, 1);  // worst case: transposed magnitude copy included
 }
 
 int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, const mst_batch_t* b, int n_iter,
@@ -491,8 +497,8 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
   if (n_iter < 0) return fail(MST_ERR_INVALID, "n_iter must be >= 0");
   if (s_layout != MST_LAYOUT_FRAME_MAJOR && s_layout != MST_LAYOUT_BIN_MAJOR) return fail(MST_ERR_INVALID, "bad layout");
   if (init_mode != 0 && init_mode != 1) return fail(MST_ERR_INVALID, "bad init_mode");
-  if (workspace_bytes < mst_griffinlim_workspace_bytes(b))
-    return fail(MST_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, mst_griffinlim_workspace_bytes(b));
+  const size_t need = mst_griffinlim_workspace_bytes_ex(b, s_layout, s_is_log1p_power);
+  if (workspace_bytes < need) return fail(MST_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
   if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return fail(MST_ERR_INVALID, "workspace must be 256-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   Tables tabs;
@@ -502,7 +508,9 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
   const size_t spec = (size_t)b->total_frames * kBins;
   char* ws = reinterpret_cast<char*>(d_workspace);
   float2* tprev = reinterpret_cast<float2*>(ws); ws += align_up((size_t)b->total_frames * kSpecStride * sizeof(float2), 256);
-  float* S_t = reinterpret_cast<float*>(ws);     ws += align_up(spec * sizeof(float), 256);
+  const bool needs_copy = s_layout != MST_LAYOUT_FRAME_MAJOR || s_is_log1p_power;
+  float* S_t = reinterpret_cast<float*>(ws);
+  if (needs_copy) ws += align_up(spec * sizeof(float), 256);
   const size_t acc_bytes = align_up((size_t)b->total_acc * sizeof(float), 256);
   float* acc[3];
   for (int i = 0; i < 3; ++i) { acc[i] = reinterpret_cast<float*>(ws); ws += acc_bytes; }

@@ -189,7 +189,7 @@ at::Tensor griffinlim(const at::Tensor& S, int64_t s_layout, bool s_is_log1p_pow
     phase = init_phase->data_ptr<float>();
   }
   at::Tensor y = at::empty({mst_batch_total_samples(b)}, S.options());
-  const size_t ws_bytes = mst_griffinlim_workspace_bytes(b);
+  const size_t ws_bytes = mst_griffinlim_workspace_bytes_ex(b, (int)s_layout, s_is_log1p_power ? 1 : 0);
   at::Tensor ws = at::empty({(int64_t)ws_bytes}, S.options().dtype(at::kByte));
   check(mst_griffinlim_f32(S.data_ptr<float>(), (int)s_layout, s_is_log1p_power ? 1 : 0, b, (int)n_iter, (float)momentum,
                            phase, (int)init_mode, (uint64_t)seed, y.data_ptr<float>(), ws.data_ptr(), ws_bytes, cur_stream()),
