@@ -128,10 +128,38 @@ __device__ __forceinline__ void fft1024_front(float2 (&v)[32], float2* scratch, 
   __syncwarp();
 }
 
-template <int SIGN>
-__device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* scratch, const float2* tw, int lane) {
-  fft1024_front<SIGN>(v, scratch, tw, lane);
-  fft32<SIGN>(v);
+// Both FFT-32 passes share ONE copy of the butterfly code (a 2-trip loop that is deliberately not unrolled): the
+// unrolled butterflies are ~600 instructions per instance and the kernels were paying instruction-cache misses.
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+// `hook` runs right after the transpose, when the scratch tile is free again and the second pass is still to come
+// (Griffin-Lim starts its asynchronous copy of the previous iterate there).
+template <int SIGN, typename Hook = NoHook>
+__device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* scratch, const float2* tw, int lane,
+                                             Hook hook = Hook()) {
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    fft32<SIGN>(v);
+    if (pass == 0) {
+#pragma unroll
+      for (int k1 = 0; k1 < 32; ++k1) {
+        float2 a = v[br5(k1)];
+        if (k1 != 0) {
+          float2 w = tw[k1 * 32 + lane];
+          if (SIGN > 0) w.y = -w.y;
+          a = cmul(a, w);
+        }
+        scratch[k1 * 33 + lane] = a;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = scratch[lane * 33 + j];
+      __syncwarp();
+      hook();
+    }
+  }
 }
 
 // ---- real <-> half-length complex conversion ("mirror layout") ------------------------------------------------
