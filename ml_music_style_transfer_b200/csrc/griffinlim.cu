@@ -45,6 +45,7 @@ struct GlParams {
   float* acc_zero;         // accumulator of launch j+1: zeroed here
   float alpha;             // momentum / (1 + momentum)
   int first_iter;          // rebuilt_0 = 0: skip the tprev read
+  int last_iter;           // nobody reads rebuilt_{n_iter}: skip the tprev write
   // init launch only
   const float* init_phase; // uniform [0,1) field or NULL
   int phase_layout;        // layout of init_phase
@@ -322,7 +323,7 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
             const int j = g8 + i;
             float2 tp = make_float2(0.0f, 0.0f);
             if (!FIRST) tp = scratch[mirror_bin(lane, kb, j)];
-            (j < 16 ? TA : TB)[32 * j] = y[j];
+            if (!P.last_iter) (j < 16 ? TA : TB)[32 * j] = y[j];
             const float ax = fmaf(-P.alpha, tp.x, y[j].x), ay = fmaf(-P.alpha, tp.y, y[j].y);
             const float sc = sm[i] * unit_scale(ax, ay);
             y[j] = make_float2(sc * ax, sc * ay);
@@ -331,7 +332,7 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
         if (lane == 0) {
           float2 tp = make_float2(0.0f, 0.0f);
           if (!FIRST) tp = scratch[512];
-          trow[512] = mid;
+          if (!P.last_iter) trow[512] = mid;
           const float ax = fmaf(-P.alpha, tp.x, mid.x), ay = fmaf(-P.alpha, tp.y, mid.y);
           const float sc = ld_stream(Srow + 512) * unit_scale(ax, ay);
           mid = make_float2(sc * ax, sc * ay);
@@ -404,7 +405,8 @@ gl_persistent_kernel(GlParams P, int n_iter, float* acc0, float* acc1, float* ac
   for (int j = 1; j <= n_iter; ++j) {
     P.acc_in = acc[cur];
     P.acc_out = acc[(cur + 1) % 3];
-    P.acc_zero = acc[(cur + 2) % 3];
+    P.acc_zero = j == n_iter ? nullptr : acc[(cur + 2) % 3];
+    P.last_iter = (j == n_iter);
     gl_tile<false, false, true>(P, m, c, cd, tile);  // tprev starts zeroed, so iteration 1 needs no special case
     grid_barrier(barrier, target);
     cur = (cur + 1) % 3;
@@ -594,8 +596,9 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
   for (int j = 1; j <= n_iter; ++j) {
     P.acc_in = acc[cur];
     P.acc_out = acc[(cur + 1) % 3];
-    P.acc_zero = acc[(cur + 2) % 3];
+    P.acc_zero = j == n_iter ? nullptr : acc[(cur + 2) % 3];  // the launch after the last one accumulates nothing
     P.first_iter = (j == 1);
+    P.last_iter = (j == n_iter);
     if (j == 1) gl_kernel<false, true><<<grid, kWarpsPerCta * 32, smem, s>>>(P);
     else gl_kernel<false, false><<<grid, kWarpsPerCta * 32, smem, s>>>(P);
     MST_CUDA_OK(cudaGetLastError());
