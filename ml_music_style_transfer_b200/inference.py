@@ -35,6 +35,19 @@ class AudioSynthesizer():
         pianoroll, onoff = notes_to_pianoroll(pitch, velocity, start, end, fs=self.wps, cc64=cc64, end_time=end_time)
         return np.transpose(pianoroll, (1, 0)), np.transpose(onoff, (1, 0))
 
+    def process_custom_midi_and_audio(self, midi_filename, audio_filename):
+        """inference.py:37-71: the model's three inputs as CUDA float tensors with a leading batch axis --
+        pianoroll (1,128,T), onoff (1,128,T), spec (1,1025,T') -- produced without leaving the device."""
+        from . import audio_io, pianoroll as _pr
+        midi_dir = os.path.join(self.exp_dir, 'midi') if self.exp_dir is not None else ''
+        pitch, velocity, start, end, cc64, end_time = read_midi(os.path.join(midi_dir, midi_filename))
+        nb = _pr.NoteBatch(pitch, velocity, start, end, [0, len(pitch)], end_times=[end_time], pedals=[cc64])
+        roll, onoff, _, _ = _pr.rasterize(nb, self.wps)
+        audio, _ = audio_io.load(audio_filename, sr=pp_hp.sr, as_numpy=False)
+        spec = process_spectrum_from_chunk(audio)  # CUDA tensor in -> CUDA (1025, T') view out
+        return (roll.t().to(torch.float32).unsqueeze(0), onoff.t().to(torch.float32).unsqueeze(0),
+                spec.contiguous().unsqueeze(0))
+
     def process_custom_audio(self, audio):
         """inference.py:54-55: whole-song log1p-power spectrogram."""
         return process_spectrum_from_chunk(audio)

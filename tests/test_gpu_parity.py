@@ -365,6 +365,25 @@ def test_load_audio_dropin(pkg, tmp_path):
         pkg.preprocess.load_audio(str(tmp_path), 2240, "upright")
 
 
+def test_process_custom_midi_and_audio_dropin(pkg, tmp_path):
+    """inference.py:37-71: device-resident model inputs from a MIDI file and a wav file."""
+    from ml_music_style_transfer_b200 import midi, synth
+    os_ = __import__("os")
+    os_.makedirs(str(tmp_path / "midi"))
+    p, v, s, e = synth.midi_piece(9, seconds=3.0)
+    midi.write_midi_notes(str(tmp_path / "midi" / "song.mid"), p, v, s, e, cc64=[(0.5, 127), (1.5, 0)])
+    x = clip(61, 44100 * 2, "noise")
+    oaudio.write_wav(str(tmp_path / "song.wav"), x, 44100, bits=32)
+    synth_ = pkg.inference.AudioSynthesizer("ckpt.tar", str(tmp_path), "song.mid", str(tmp_path / "song.wav"))
+    roll, onoff, spec = synth_.process_custom_midi_and_audio("song.mid", str(tmp_path / "song.wav"))
+    assert roll.is_cuda and roll.dtype == torch.float32 and roll.shape[:2] == (1, 128) and onoff.shape == roll.shape
+    assert spec.shape == (1, 1025, 1 + len(x) // 256)
+    rp, rv, rs, re_, cc, end_time = midi.read_midi(str(tmp_path / "midi" / "song.mid"))
+    ref_r, ref_o = opp.midi_notes_to_pianoroll(rp, rv, rs, re_, cc64=cc, end_time=end_time)
+    assert np.array_equal(roll[0].cpu().numpy(), ref_r.T) and np.array_equal(onoff[0].cpu().numpy(), ref_o.T)
+    assert_close(spec[0].cpu().numpy(), opp.process_spectrum_from_chunk(x).astype(np.float64))
+
+
 def test_get_data_end_to_end(pkg, tmp_path):
     """preprocess.py:163-200 on one synthetic song: midi + two style wavs -> shard dataset -> training items."""
     from ml_music_style_transfer_b200 import midi, synth
