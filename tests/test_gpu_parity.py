@@ -637,6 +637,9 @@ def test_full_size_properties(pkg, gpu):
         per_col = torch.bincount(cols[cols < T], minlength=T).to(torch.int64)
         want = (roll[ro[i]:ro[i + 1], 21:109].to(torch.int64) * per_col[:, None]).sum(0)
         assert torch.equal(up[i].to(torch.int64).sum(-1), want)
+        # on/off is the time derivative of the roll: integrating it gives the roll back (roll -> events -> roll round trip,
+        # the property behind the reference's utils/pretty_midi_roll_to_midi.py)
+        assert torch.equal(torch.cumsum(onoff[ro[i]:ro[i + 1]].to(torch.int32), 0), roll[ro[i]:ro[i + 1]].to(torch.int32))
     # (5) Griffin-Lim at scale is a fixed point on consistent spectrograms: true phase in, 2 iterations, signal back
     nb = 256
     gb = F.ClipBatch.from_frames([bench.T_FRAMES] * nb, bench.HOP, device=gpu)
