@@ -42,7 +42,7 @@ def clip(seed, n, kind="piano"):
 # ---- P1: STFT ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("hop", [256, 512])
 @pytest.mark.parametrize("pad", ["reflect", "constant"])
-@pytest.mark.parametrize("n", [88200, 30001, 2049])
+@pytest.mark.parametrize("n", [88200, 30001, 2049, 1025])
 def test_stft_complex(pkg, hop, pad, n):
     y = clip(n, n, "noise" if n == 30001 else "piano")
     D = pkg.features.stft(y, hop_length=hop, pad_mode=pad)
