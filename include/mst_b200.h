@@ -76,6 +76,8 @@ void mst_batch_destroy(mst_batch_t* b);
 int mst_batch_n_clips(const mst_batch_t* b);
 int64_t mst_batch_total_frames(const mst_batch_t* b);
 int64_t mst_batch_total_samples(const mst_batch_t* b); /* sum of clip lengths */
+int64_t mst_batch_audio_extent(const mst_batch_t* b);  /* max(clip offset + length): floats the audio buffer must hold */
+int mst_batch_device(const mst_batch_t* b);            /* CUDA device the descriptor tables live on */
 int64_t mst_batch_clip_frames(const mst_batch_t* b, int clip);
 int64_t mst_batch_frame_offset(const mst_batch_t* b, int clip); /* prefix sum of frames */
 
@@ -136,6 +138,23 @@ int mst_pianoroll_rasterize_sustain(const int32_t* d_pitch, const int32_t* d_vel
                                     const int32_t* d_span_piece, const int64_t* d_span_start, const int64_t* d_span_end,
                                     int n_spans, uint8_t* d_roll, int8_t* d_onoff, int32_t* d_velsum,
                                     mst_stream_t stream);
+/* PrettyMIDI.get_piano_roll over a whole file (preprocess.py:146-147, inference.py:40-41 call it on files that may
+ * hold several instruments): the per-instrument velocity sums (d_velsum, already through the CC64 rule, one "piece" per
+ * instrument, rows d_inst_row_offsets) get their pitch bends applied and are summed, in instrument order, into the
+ * widest roll of their file.  Bend segment = one (start_bend, end_bend) pair of pretty_midi's loop with |pitch| >= 1:
+ * columns [c0, c1), bend_int, bend_decimal d and m1 = 1 - d (float64, evaluated by the host exactly as Python does),
+ * positive = (pitch >= 0).  Segments of an instrument are sorted and disjoint (d_seg_offsets: int32[n_instruments+1]).
+ * Outputs: d_out_f64 (optional, [total_rows][128] float64 = get_piano_roll(fs).T), d_roll = (value != 0), d_onoff. */
+typedef struct mst_bend_segment {
+  int64_t c0, c1;
+  double d, m1;
+  int32_t bend_int;
+  int32_t positive;
+} mst_bend_segment_t;
+int mst_pianoroll_merge_instruments(const int32_t* d_velsum, const int64_t* d_inst_row_offsets, const int32_t* d_inst_is_drum,
+                                    int n_instruments, const int32_t* d_file_inst_offsets, const int64_t* d_file_row_offsets,
+                                    int n_files, int64_t total_rows, const int32_t* d_seg_offsets, const void* d_segments,
+                                    double* d_out_f64, uint8_t* d_roll, int8_t* d_onoff, mst_stream_t stream);
 /* preprocess.py:80-96: out[c][j][p] = plane[c*stride_rows + j][p], j < chunk_rows; rows beyond
  * n_rows read as 0.  in: int8/uint8 plane; out_dtype MST_DTYPE_{I8,F32,F64} (reference: float64). */
 int mst_pianoroll_chunks(const void* d_plane, int64_t n_rows, int num_chunks, int chunk_rows, int stride_rows,

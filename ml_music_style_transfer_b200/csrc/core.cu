@@ -98,6 +98,9 @@ static int batch_finish(mst_batch* b) {
     if (tile_off > 0x7fffffff) return fail(MST_ERR_INVALID, "too many frame tiles in one batch");
   }
   b->total_frames = frame_off;
+  b->audio_extent = 0;
+  for (int c = 0; c < b->n_clips; ++c)
+    b->audio_extent = std::max(b->audio_extent, b->h_clips[c].sample_offset + b->h_clips[c].length);
   b->total_samples = samples;
   b->total_acc = acc_off;
   b->total_tiles = (int)tile_off;
@@ -252,6 +255,8 @@ void mst_batch_destroy(mst_batch_t* b) {
 int mst_batch_n_clips(const mst_batch_t* b) { return b ? b->n_clips : 0; }
 int64_t mst_batch_total_frames(const mst_batch_t* b) { return b ? b->total_frames : 0; }
 int64_t mst_batch_total_samples(const mst_batch_t* b) { return b ? b->total_samples : 0; }
+int64_t mst_batch_audio_extent(const mst_batch_t* b) { return b ? b->audio_extent : 0; }
+int mst_batch_device(const mst_batch_t* b) { return b ? b->device : -1; }
 int64_t mst_batch_clip_frames(const mst_batch_t* b, int c) { return (b && c >= 0 && c < b->n_clips) ? b->h_clips[c].frames : -1; }
 int64_t mst_batch_frame_offset(const mst_batch_t* b, int c) {
   if (!b || c < 0 || c > b->n_clips) return -1;

@@ -21,6 +21,7 @@
 // e.g. a single clip): gl_persistent_kernel runs the whole loop in ONE cooperative launch with a grid-wide barrier
 // between iterations.
 #include <algorithm>
+#include <atomic>
 #include "fft_warp.cuh"
 #include "mst_common.cuh"
 
@@ -536,12 +537,13 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
   MST_CUDA_OK(cudaGetDevice(&dev));
   MST_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t smem = kGlSmemBytes;
-  static bool attr_set[64] = {false};
-  if (!attr_set[dev]) {
+  if (dev < 0 || dev >= 64) return fail(MST_ERR_INVALID, "device index %d out of range", dev);
+  static std::atomic<bool> attr_set[64];  // setting the attribute twice is harmless; the flag itself must not race
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[dev] = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
   const int grid = std::min(b->total_tiles, 2 * sms);
 
@@ -561,19 +563,19 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
 
   // Small batch: every tile can be resident at once -> one cooperative persistent kernel for the whole loop.
   {
-    static int coop_ok[64] = {0};  // 0 unknown, 1 usable, -1 not
-    if (coop_ok[dev] == 0) {
+    static std::atomic<int> coop_ok[64];  // 0 unknown, 1 usable, -1 not
+    if (coop_ok[dev].load(std::memory_order_acquire) == 0) {
       int coop = 0, per_sm = 0;
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
       if (coop && cudaFuncSetAttribute(gl_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gl_persistent_kernel, kWarpsPerCta * 32, smem) == cudaSuccess &&
           per_sm >= 2)
-        coop_ok[dev] = 1;
+        coop_ok[dev].store(1, std::memory_order_release);
       else
-        coop_ok[dev] = -1;
+        coop_ok[dev].store(-1, std::memory_order_release);
       cudaGetLastError();
     }
-    if (coop_ok[dev] == 1 && b->total_tiles <= 2 * sms) {
+    if (coop_ok[dev].load(std::memory_order_acquire) == 1 && b->total_tiles <= 2 * sms) {
       unsigned int* barrier = reinterpret_cast<unsigned int*>(ws);  // the 256 spare bytes at the end of the workspace
       MST_CUDA_OK(cudaMemsetAsync(barrier, 0, 256, s));
       MST_CUDA_OK(cudaMemsetAsync(tprev, 0, (size_t)b->total_frames * kSpecStride * sizeof(float2), s));

@@ -52,6 +52,7 @@ struct mst_batch {
   int n_clips = 0;
   int n_fft = 0, hop = 0, pad_mode = 0;
   int64_t total_frames = 0, total_samples = 0, total_acc = 0;
+  int64_t audio_extent = 0;          // max over clips of sample_offset + length: elements the audio buffer must hold
   int total_tiles = 0;
   int uniform_frames = 0;            // frames per clip when every clip has the same length, else 0
   int device = 0;

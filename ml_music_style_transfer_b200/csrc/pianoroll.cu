@@ -113,6 +113,73 @@ __global__ void onoff_kernel(const uint8_t* __restrict__ roll, const int64_t* __
   }
 }
 
+// PrettyMIDI.get_piano_roll over several instruments (pretty_midi 0.2.9): every instrument's velocity-sum roll (already
+// sustained) gets its pitch bends applied -- each bend segment [c0, c1) shifts the rows by the integer part of the bend
+// and linearly interpolates by the fractional part, in float64 with NumPy's rounding sequence (two products, one sum,
+// no FMA) -- and the instruments of a file are then summed, in instrument order, into the widest roll.  Drum
+// instruments contribute zeros (but their width counts).  One thread per (file row, pitch): a column of an instrument
+// lies in at most one bend segment, so every output cell is a pure function of the un-bent column.
+struct BendSeg {
+  int64_t c0, c1;   // columns [c0, c1) of the instrument's roll
+  double d, m1;     // bend_decimal and (1 - bend_decimal), both evaluated on the host in float64
+  int32_t bi;       // bend_int (signed)
+  int32_t positive; // start_bend.pitch >= 0
+};
+
+__device__ __forceinline__ double bent_value(const int32_t* __restrict__ col, int r, const BendSeg& sg) {
+  // B[q] = piano_roll[q - bi] where that row exists (the shifted copy), 0 elsewhere
+  auto B = [&](int q) -> double {
+    const int src = q - sg.bi;
+    if (sg.bi > 0 && q < sg.bi) return 0.0;
+    if (sg.bi < 0 && q >= 128 + sg.bi) return 0.0;
+    return (src >= 0 && src < 128) ? (double)col[src] : 0.0;
+  };
+  if (sg.positive) {
+    if (r == 0) return B(0);
+    return __dadd_rn(__dmul_rn(sg.m1, B(r)), __dmul_rn(sg.d, B(r - 1)));
+  }
+  if (r == 127) return B(127);
+  return __dadd_rn(__dmul_rn(sg.m1, B(r)), __dmul_rn(sg.d, B(r + 1)));
+}
+
+__global__ void merge_instruments_kernel(const int32_t* __restrict__ velsum, const int64_t* __restrict__ inst_row_off,
+                                         const int32_t* __restrict__ inst_is_drum, const int32_t* __restrict__ file_inst_off,
+                                         const int64_t* __restrict__ file_row_off, int n_files,
+                                         const int32_t* __restrict__ seg_off, const BendSeg* __restrict__ segs,
+                                         int64_t total_rows, double* __restrict__ out_f64, uint8_t* __restrict__ roll) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gid >> 7;
+  const int p = (int)(gid & 127);
+  if (row >= total_rows) return;
+  int lo = 0, hi = n_files;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (file_row_off[mid] <= row) lo = mid; else hi = mid;
+  }
+  const int64_t col = row - file_row_off[lo];
+  double acc = 0.0;
+  for (int i = file_inst_off[lo]; i < file_inst_off[lo + 1]; ++i) {
+    const int64_t r0 = inst_row_off[i], T = inst_row_off[i + 1] - r0;
+    if (col >= T) continue;
+    double v = 0.0;
+    if (!inst_is_drum[i]) {
+      const int32_t* c = velsum + (r0 + col) * 128;
+      int a = seg_off[i], b = seg_off[i + 1];  // segments are sorted and disjoint: find the one with c0 <= col < c1
+      const BendSeg* hit = nullptr;
+      while (a < b) {
+        const int m = (a + b) >> 1;
+        if (segs[m].c1 <= col) a = m + 1;
+        else if (segs[m].c0 > col) b = m;
+        else { hit = segs + m; break; }
+      }
+      v = hit ? bent_value(c, p, *hit) : (double)c[p];
+    }
+    acc = __dadd_rn(acc, v);
+  }
+  if (out_f64) out_f64[row * 128 + p] = acc;
+  roll[row * 128 + p] = acc != 0.0 ? 1 : 0;
+}
+
 template <typename OUT>
 __global__ void chunks_kernel(const int8_t* __restrict__ plane, int64_t n_rows, int num_chunks, int chunk_rows,
                               int stride_rows, OUT* __restrict__ out) {
@@ -322,6 +389,29 @@ int mst_pianoroll_rasterize(const int32_t* d_pitch, const int32_t* d_velocity, c
   onoff_kernel<<<grid, 256, 0, s>>>(d_roll, d_row_offsets, n_pieces, d_onoff);
   MST_CUDA_OK(cudaGetLastError());
   count_launch();
+  return MST_OK;
+}
+
+int mst_pianoroll_merge_instruments(const int32_t* d_velsum, const int64_t* d_inst_row_offsets, const int32_t* d_inst_is_drum,
+                                    int n_instruments, const int32_t* d_file_inst_offsets, const int64_t* d_file_row_offsets,
+                                    int n_files, int64_t total_rows, const int32_t* d_seg_offsets, const void* d_segments,
+                                    double* d_out_f64, uint8_t* d_roll, int8_t* d_onoff, mst_stream_t stream) {
+  if (n_files <= 0 || n_instruments < 0 || total_rows < 0) return fail(MST_ERR_INVALID, "bad sizes");
+  if (total_rows == 0) return MST_OK;
+  if (!d_inst_row_offsets || !d_inst_is_drum || !d_file_inst_offsets || !d_file_row_offsets || !d_seg_offsets || !d_roll ||
+      !d_onoff || (!d_velsum && n_instruments > 0))
+    return fail(MST_ERR_INVALID, "null argument");
+  static_assert(sizeof(BendSeg) == 40, "BendSeg layout is part of the ABI (include/mst_b200.h: mst_bend_segment_t)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t threads = total_rows * 128;
+  merge_instruments_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+      d_velsum, d_inst_row_offsets, d_inst_is_drum, d_file_inst_offsets, d_file_row_offsets, n_files, d_seg_offsets,
+      reinterpret_cast<const BendSeg*>(d_segments), total_rows, d_out_f64, d_roll);
+  MST_CUDA_OK(cudaGetLastError());
+  dim3 grid(64, (unsigned)std::min(n_files, 65535));
+  onoff_kernel<<<grid, 256, 0, s>>>(d_roll, d_file_row_offsets, n_files, d_onoff);
+  MST_CUDA_OK(cudaGetLastError());
+  count_launch(2);
   return MST_OK;
 }
 

@@ -6,6 +6,7 @@
 // Replaces librosa.stft + np.log1p(np.abs(.)**2) (reference preprocessing/preprocess.py:47-57) and, together with
 // mel_gemm.cu, librosa.feature.melspectrogram (reference tests/plot_spec.py:20).
 #include <algorithm>
+#include <atomic>
 #include <vector>
 #include "fft_warp.cuh"
 #include "mel_plan.cuh"
@@ -241,13 +242,13 @@ static int launch_stft(const float* d_audio, const mst_batch* b, int layout, voi
   int rc = get_tables(&tabs);
   if (rc) return rc;
   const size_t smem = kStftSmemBytes;
-  static bool attr_set[64] = {false};
+  static std::atomic<bool> attr_set[64];  // one flag per device and per MODE instantiation
   int dev = 0;
   MST_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(MST_ERR_INVALID, "device index %d out of range", dev);
-  if (!attr_set[dev]) {
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     MST_CUDA_OK(cudaFuncSetAttribute(stft_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[dev] = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
   int sms = 0;
   MST_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -15,6 +15,14 @@ void check(int rc, const char* what) {
 }
 mst_stream_t cur_stream() { return reinterpret_cast<mst_stream_t>(at::cuda::getCurrentCUDAStream().stream()); }
 mst_batch_t* as_batch(int64_t h) { TORCH_CHECK(h != 0, "null batch handle"); return reinterpret_cast<mst_batch_t*>(h); }
+// A batch handle indexes the audio / waveform tensor it is used with: refuse tensors that are too small or live on
+// another device instead of letting a kernel read out of bounds.
+void check_batch_audio(const mst_batch_t* b, const at::Tensor& t, const char* name) {
+  TORCH_CHECK(mst_batch_device(b) == (int)t.get_device(), "the batch handle was built on cuda:", mst_batch_device(b), " but ",
+              name, " lives on cuda:", (int)t.get_device());
+  TORCH_CHECK(t.numel() >= mst_batch_audio_extent(b), name, " has ", t.numel(), " samples but the batch's clips reach ",
+              mst_batch_audio_extent(b));
+}
 mst_mel_plan_t* as_plan(int64_t h) { TORCH_CHECK(h != 0, "null mel plan handle"); return reinterpret_cast<mst_mel_plan_t*>(h); }
 void want(const at::Tensor& t, at::ScalarType st, const char* name) {
   TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
@@ -72,6 +80,7 @@ at::Tensor stft(const at::Tensor& audio, int64_t batch, int64_t out_mode, int64_
   want(audio, at::kFloat, "audio");
   c10::cuda::CUDAGuard guard(audio.device());
   mst_batch_t* b = as_batch(batch);
+  check_batch_audio(b, audio, "audio");
   const int64_t F = mst_batch_total_frames(b);
   at::Tensor out = out_mode == MST_OUT_COMPLEX ? at::empty({F, 1025}, audio.options().dtype(at::kComplexFloat))
                                                : at::empty({F * 1025}, audio.options());
@@ -84,6 +93,7 @@ at::Tensor stft_mel(const at::Tensor& audio, int64_t batch, int64_t plan, int64_
   c10::cuda::CUDAGuard guard(audio.device());
   mst_batch_t* b = as_batch(batch);
   mst_mel_plan_t* p = as_plan(plan);
+  check_batch_audio(b, audio, "audio");
   const int64_t F = mst_batch_total_frames(b);
   at::Tensor out = at::empty({F * n_mels}, audio.options());
   const size_t ws_bytes = mst_stft_mel_workspace_bytes(b, p);
@@ -141,6 +151,32 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> pianoroll_rasterize(const at::Ten
   return {roll, onoff, velsum};
 }
 
+std::tuple<at::Tensor, at::Tensor, at::Tensor> pianoroll_merge_instruments(
+    const at::Tensor& velsum, const at::Tensor& inst_row_offsets, const at::Tensor& inst_is_drum,
+    const at::Tensor& file_inst_offsets, const at::Tensor& file_row_offsets, int64_t total_rows,
+    const at::Tensor& seg_offsets, const at::Tensor& segments, bool want_f64) {
+  want(velsum, at::kInt, "velsum"); want(inst_row_offsets, at::kLong, "inst_row_offsets");
+  want(inst_is_drum, at::kInt, "inst_is_drum"); want(file_inst_offsets, at::kInt, "file_inst_offsets");
+  want(file_row_offsets, at::kLong, "file_row_offsets"); want(seg_offsets, at::kInt, "seg_offsets");
+  want(segments, at::kByte, "segments");
+  c10::cuda::CUDAGuard guard(velsum.device());
+  const int64_t n_inst = inst_is_drum.numel(), n_files = file_row_offsets.numel() - 1;
+  TORCH_CHECK(inst_row_offsets.numel() == n_inst + 1 && seg_offsets.numel() == n_inst + 1 &&
+              file_inst_offsets.numel() == n_files + 1, "offset arrays do not match the instrument / file counts");
+  TORCH_CHECK(segments.numel() % (int64_t)sizeof(mst_bend_segment_t) == 0, "segments must be packed mst_bend_segment_t");
+  at::Tensor out = want_f64 ? at::empty({total_rows, 128}, velsum.options().dtype(at::kDouble))
+                            : at::empty({0}, velsum.options().dtype(at::kDouble));
+  at::Tensor roll = at::empty({total_rows, 128}, velsum.options().dtype(at::kByte));
+  at::Tensor onoff = at::empty({total_rows, 128}, velsum.options().dtype(at::kChar));
+  check(mst_pianoroll_merge_instruments(velsum.data_ptr<int32_t>(), inst_row_offsets.data_ptr<int64_t>(),
+                                        inst_is_drum.data_ptr<int32_t>(), (int)n_inst, file_inst_offsets.data_ptr<int32_t>(),
+                                        file_row_offsets.data_ptr<int64_t>(), (int)n_files, total_rows,
+                                        seg_offsets.data_ptr<int32_t>(), segments.data_ptr(),
+                                        want_f64 ? out.data_ptr<double>() : nullptr, roll.data_ptr<uint8_t>(),
+                                        onoff.data_ptr<int8_t>(), cur_stream()), "mst_pianoroll_merge_instruments");
+  return {roll, onoff, out};
+}
+
 at::ScalarType dtype_of(int64_t code) {
   switch (code) {
     case MST_DTYPE_I8: return at::kChar;
@@ -180,6 +216,8 @@ at::Tensor griffinlim(const at::Tensor& S, int64_t s_layout, bool s_is_log1p_pow
   want(S, at::kFloat, "S");
   c10::cuda::CUDAGuard guard(S.device());
   mst_batch_t* b = as_batch(batch);
+  TORCH_CHECK(mst_batch_device(b) == (int)S.get_device(), "the batch handle was built on cuda:", mst_batch_device(b),
+              " but S lives on cuda:", (int)S.get_device());
   TORCH_CHECK(S.numel() == mst_batch_total_frames(b) * 1025, "S has ", S.numel(), " elements, batch expects ",
               mst_batch_total_frames(b) * 1025);
   const float* phase = nullptr;
@@ -202,6 +240,8 @@ at::Tensor spectral_convergence(const at::Tensor& y, int64_t batch, const at::Te
   want(S, at::kFloat, "S");
   c10::cuda::CUDAGuard guard(y.device());
   mst_batch_t* b = as_batch(batch);
+  check_batch_audio(b, y, "y");
+  TORCH_CHECK(S.get_device() == y.get_device(), "S and y live on different devices");
   TORCH_CHECK(S.numel() == mst_batch_total_frames(b) * 1025, "S does not match the batch");
   const int64_t n = mst_batch_n_clips(b);
   at::Tensor sums = at::empty({2, n}, y.options().dtype(at::kDouble));
@@ -243,6 +283,8 @@ TORCH_LIBRARY(mst_b200, m) {
   m.def("pianoroll_rasterize(Tensor pitch, Tensor velocity, Tensor start, Tensor end, Tensor note_offsets, "
         "Tensor row_offsets, int total_rows, int fs, bool want_velsum, Tensor? span_piece, Tensor? span_start, "
         "Tensor? span_end) -> (Tensor, Tensor, Tensor)");
+  m.def("pianoroll_merge_instruments(Tensor velsum, Tensor inst_row_offsets, Tensor inst_is_drum, Tensor file_inst_offsets, "
+        "Tensor file_row_offsets, int total_rows, Tensor seg_offsets, Tensor segments, bool want_f64) -> (Tensor, Tensor, Tensor)");
   m.def("pianoroll_chunks(Tensor plane, int num_chunks, int chunk_rows, int stride_rows, int out_dtype) -> Tensor");
   m.def("pianoroll_upsample(Tensor plane, Tensor row_offsets, Tensor sample_offsets, int total_samples, int fs, int sr, "
         "int pitch_lo, int n_keys, int out_dtype) -> Tensor");
@@ -257,6 +299,7 @@ TORCH_LIBRARY_IMPL(mst_b200, CUDA, m) {
   m.impl("stft_mel", &stft_mel);
   m.impl("pianoroll_count_rows", &pianoroll_count_rows);
   m.impl("pianoroll_rasterize", &pianoroll_rasterize);
+  m.impl("pianoroll_merge_instruments", &pianoroll_merge_instruments);
   m.impl("pianoroll_chunks", &pianoroll_chunks);
   m.impl("pianoroll_upsample", &pianoroll_upsample);
   m.impl("griffinlim", &griffinlim);

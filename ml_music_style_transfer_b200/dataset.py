@@ -23,18 +23,41 @@ class ShardManager():
     FloatTensor conversion of train.py:93-99, 8x / 2x smaller); ``dtype='float64'`` stores what the reference stores.
     """
 
-    def __init__(self, root, dtype="native"):
-        self.root = root
-        self.dtype = dtype
-        os.makedirs(root, exist_ok=True)
+    def __init__(self, root, dtype=None, mode="a"):
+        """mode 'w' truncates like the reference's ``h5py.File(outfile, 'w')`` (io_manager.py:41), 'a' appends to an
+        existing container, 'r' opens an existing one read-only.  ``dtype`` None = whatever the container holds
+        ('native' for a new one); an explicit dtype that contradicts an existing container raises."""
+        if mode not in ("w", "a", "r"):
+            raise ValueError(f"mode={mode!r} (w | a | r)")
+        self.root, self.mode = root, mode
         self.index_path = os.path.join(root, "index.json")
+        if mode == "r" and not os.path.exists(self.index_path):
+            raise FileNotFoundError(self.index_path)
+        os.makedirs(root, exist_ok=True)
+        if mode == "w" and os.path.exists(self.index_path):
+            with open(self.index_path) as f:
+                old = json.load(f)
+            for entries in old.get("keys", {}).values():      # drop the shards the old index owns, nothing else
+                for e in entries:
+                    try:
+                        os.remove(os.path.join(root, e["file"]))
+                    except FileNotFoundError:
+                        pass
+            os.remove(self.index_path)
         if os.path.exists(self.index_path):
             with open(self.index_path) as f:
                 self.index = json.load(f)
+            if dtype is not None and dtype != self.index["dtype"]:
+                raise ValueError(f"container at {root} holds dtype={self.index['dtype']!r}, asked for {dtype!r}")
         else:
-            self.index = {"dtype": dtype, "keys": {}}
+            self.index = {"dtype": dtype or "native", "keys": {}}
+        self.dtype = self.index["dtype"]
+        if self.dtype not in ("native", "float64"):
+            raise ValueError(f"dtype={self.dtype!r} (native | float64)")
 
     def _append(self, key, arr, native):
+        if self.mode == "r":
+            raise IOError("container opened read-only")
         arr = np.asarray(arr)
         arr = arr.astype(np.float64 if self.dtype == "float64" else native, copy=False)
         entries = self.index["keys"].setdefault(key, [])
@@ -76,18 +99,35 @@ class ShardManager():
 class ShardDataset(torch.utils.data.Dataset):
     """Drop-in for train.py::Dataseth5py (train.py:45-104) over a ShardManager directory."""
 
-    def __init__(self, in_dir, seed=42, n_read=None, device=None):
+    def __init__(self, in_dir, seed=42, n_read=None, device=None, resident=None):
+        """``resident`` (default: True when ``device`` is a CUDA device): upload every array ONCE and serve items
+        straight from GPU memory -- int8 rolls and float32 spectrograms stay in HBM (a 100-chunk song is 22 MB of rolls
+        and 353 MB per style), an item is two gathers and a transposed cast on the device, nothing crosses PCIe per
+        item (the reference builds ``torch.cuda.FloatTensor(item)`` from host arrays on every access, train.py:93-99)."""
         super(ShardDataset, self).__init__()
-        self.manager = ShardManager(in_dir)
+        self.manager = ShardManager(in_dir, mode="r")
         self.styles = [name for name in self.manager.keys() if 'spec_' in name]
         self.pianoroll = self.manager.read('pianoroll', n_read)
         self.onoff = self.manager.read('onoff', n_read)
         self.specs = {style: self.manager.read(style, n_read) for style in self.styles}
         self.n_data = self.pianoroll.shape[0]
-        self.device = device
+        self.device = None if device is None else torch.device(device)
+        self.resident = (self.device is not None and self.device.type == "cuda") if resident is None else bool(resident)
+        if self.resident:
+            if self.device is None or self.device.type != "cuda":
+                raise ValueError("resident=True needs a CUDA device")
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+            self.pianoroll, self.onoff = up(self.pianoroll), up(self.onoff)
+            self.specs = {k: up(v) for k, v in self.specs.items()}
         random.seed(seed)
 
     def __getitem__(self, index):
+        if self.resident:
+            # same RNG call order as the host path below (train.py:76-101): style first, then the conditioning index
+            style = random.choice(self.styles)
+            rand_index = random.randint(0, self.n_data - 1)
+            X = torch.cat((self.pianoroll[index], self.onoff[index]), dim=-1).t().to(torch.float32).contiguous()
+            return X, self.specs[style][rand_index].to(torch.float32), self.specs[style][index].to(torch.float32)
         pianoroll = np.concatenate((self.pianoroll[index], self.onoff[index]), axis=-1)
         pianoroll = np.transpose(pianoroll, (1, 0))
         style = random.choice(self.styles)

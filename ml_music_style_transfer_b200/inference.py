@@ -10,7 +10,7 @@ import torch
 
 from . import _lib, features
 from .preprocess import hyperparams, notes_to_pianoroll, process_spectrum_from_chunk
-from .midi import read_midi
+from .midi import read_midi_file
 
 pp_hp = hyperparams()
 
@@ -27,22 +27,23 @@ class AudioSynthesizer():
 
     @property
     def checkpoint(self):
-        return torch.load(os.path.join(self.exp_dir, self._checkpoint_name))
+        if getattr(self, "_checkpoint", None) is None:  # read once, like the attribute the reference sets in __init__
+            self._checkpoint = torch.load(os.path.join(self.exp_dir, self._checkpoint_name))
+        return self._checkpoint
 
     def process_custom_midi(self, midi_path):
         """inference.py:39-51: (pianoroll, onoff) transposed to (128, T)."""
-        pitch, velocity, start, end, cc64, end_time = read_midi(midi_path)
-        pianoroll, onoff = notes_to_pianoroll(pitch, velocity, start, end, fs=self.wps, cc64=cc64, end_time=end_time)
-        return np.transpose(pianoroll, (1, 0)), np.transpose(onoff, (1, 0))
+        from . import pianoroll as _pr
+        roll, onoff, _, _ = _pr.midi_to_pianoroll(read_midi_file(midi_path), self.wps)
+        return (np.transpose(roll.to(torch.float64).cpu().numpy(), (1, 0)),
+                np.transpose(onoff.to(torch.float64).cpu().numpy(), (1, 0)))
 
     def process_custom_midi_and_audio(self, midi_filename, audio_filename):
         """inference.py:37-71: the model's three inputs as CUDA float tensors with a leading batch axis --
         pianoroll (1,128,T), onoff (1,128,T), spec (1,1025,T') -- produced without leaving the device."""
         from . import audio_io, pianoroll as _pr
         midi_dir = os.path.join(self.exp_dir, 'midi') if self.exp_dir is not None else ''
-        pitch, velocity, start, end, cc64, end_time = read_midi(os.path.join(midi_dir, midi_filename))
-        nb = _pr.NoteBatch(pitch, velocity, start, end, [0, len(pitch)], end_times=[end_time], pedals=[cc64])
-        roll, onoff, _, _ = _pr.rasterize(nb, self.wps)
+        roll, onoff, _, _ = _pr.midi_to_pianoroll(read_midi_file(os.path.join(midi_dir, midi_filename)), self.wps)
         audio, _ = audio_io.load(audio_filename, sr=pp_hp.sr, as_numpy=False)
         spec = process_spectrum_from_chunk(audio)  # CUDA tensor in -> CUDA (1025, T') view out
         return (roll.t().to(torch.float32).unsqueeze(0), onoff.t().to(torch.float32).unsqueeze(0),

@@ -121,6 +121,73 @@ def get_piano_roll(pitch, velocity, start, end, fs=100, cc64=None, end_time=None
     return velsum.t().to(torch.float64).cpu().numpy()
 
 
+def bend_segments(pitch_bends, end_time, fs):
+    """pretty_midi's bend loop (Instrument.get_piano_roll) reduced to its active segments: for consecutive bends
+    (sorted by time, a zero bend appended at ``end_time``) with |pitch| >= 1 and a non-empty column range ->
+    (c0, c1, d, 1 - d, bend_int, positive).  All scalars are evaluated here exactly as Python evaluates them."""
+    ordered = sorted(pitch_bends, key=lambda b: b[1])
+    segs = []
+    for (pitch, t0), (_, t1) in zip(ordered, ordered[1:] + [(0, end_time)]):
+        if abs(pitch) < 1:
+            continue
+        c0, c1 = int(t0 * fs), int(t1 * fs)
+        if c1 <= c0:
+            continue
+        semis = 2.0 * pitch / 8192.0
+        bend_int = int(np.sign(semis) * np.floor(np.abs(semis)))
+        d = float(np.abs(semis - bend_int))
+        segs.append((c0, c1, d, 1 - d, bend_int, 1 if pitch >= 0 else 0))
+    return segs
+
+
+_SEG_DTYPE = np.dtype([("c0", "<i8"), ("c1", "<i8"), ("d", "<f8"), ("m1", "<f8"), ("bi", "<i4"), ("pos", "<i4")])
+
+
+def midi_to_pianoroll(midi_files, fs, pedal_threshold=64, want_f64=False, device=None):
+    """``PrettyMIDI.get_piano_roll(fs).T`` -> binarise -> on/off for parsed MIDI files (``midi.read_midi_file``), with
+    pretty_midi's full semantics: one roll per instrument (its own CC64 sustain spans and pitch bends, drums zero),
+    summed in instrument order into the widest roll (preprocess.py:146-155, inference.py:40-51).
+
+    Returns (roll uint8 [sum T, 128], onoff int8, row_offsets int64 [n_files + 1], velsum float64 | None).
+    """
+    device = _lib.require_cuda(device)
+    if not isinstance(midi_files, (list, tuple)):
+        midi_files = [midi_files]
+    insts, file_inst_off = [], [0]
+    for mf in midi_files:
+        insts += list(mf.instruments)
+        file_inst_off.append(len(insts))
+    n_files = len(midi_files)
+    file_rows = []
+    for f in range(n_files):
+        mine = insts[file_inst_off[f]:file_inst_off[f + 1]]
+        file_rows.append(max([int(fs * i.get_end_time()) if i.n_notes else 0 for i in mine], default=0))
+    file_row_off = np.zeros(n_files + 1, dtype=np.int64)
+    np.cumsum(file_rows, out=file_row_off[1:])
+    total_rows = int(file_row_off[-1])
+    if not insts or total_rows == 0:
+        z = torch.zeros((total_rows, 128), dtype=torch.uint8, device=device)
+        return z, z.to(torch.int8), torch.from_numpy(file_row_off).to(device), (z.to(torch.float64) if want_f64 else None)
+    # one "piece" per instrument through the note rasteriser + CC64 rule (drums keep their width but get no notes)
+    empty = (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float64), np.zeros(0, np.float64))
+    nb = NoteBatch.from_pieces([empty if i.is_drum else i.arrays() for i in insts], device=device)
+    nb.end_times = [i.get_end_time() if i.n_notes else 0.0 for i in insts]
+    nb.pedals = [[] if i.is_drum else i.cc64() for i in insts]
+    _, _, inst_row_off, velsum = rasterize(nb, fs, want_velsum=True, pedal_threshold=pedal_threshold)
+    seg_off, segs = [0], []
+    for i in insts:
+        if not i.is_drum and i.n_notes:
+            segs += bend_segments(i.pitch_bends, i.get_end_time(), fs)
+        seg_off.append(len(segs))
+    seg_np = np.array(segs, dtype=_SEG_DTYPE) if segs else np.zeros(0, dtype=_SEG_DTYPE)
+    dev_i32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.int32)).to(device)
+    seg_bytes = torch.from_numpy(np.frombuffer(seg_np.tobytes() or b"\0" * _SEG_DTYPE.itemsize, dtype=np.uint8).copy()).to(device)
+    roll, onoff, out = _lib.ops().pianoroll_merge_instruments(
+        velsum.contiguous(), inst_row_off, dev_i32([1 if i.is_drum else 0 for i in insts]), dev_i32(file_inst_off),
+        torch.from_numpy(file_row_off).to(device), total_rows, dev_i32(seg_off), seg_bytes, bool(want_f64))
+    return roll, onoff, torch.from_numpy(file_row_off).to(device), (out if want_f64 else None)
+
+
 def chunks(plane, num_chunks, chunk_rows, stride_rows, dtype=torch.float64):
     """preprocess.py:80-96 on the device: (num_chunks, chunk_rows, 128)."""
     return _lib.ops().pianoroll_chunks(plane, int(num_chunks), int(chunk_rows), int(stride_rows), DTYPE_CODES[dtype])

@@ -42,40 +42,54 @@ class HostPipeline:
             self.chunks.append(dict(a0=a0, a1=a1, m=a1 - a0,
                                     batch=F.ClipBatch.uniform(a1 - a0, self.clip_len, self.hop, device=self.device),
                                     gl_batch=F.ClipBatch.from_frames([self.frames] * (a1 - a0), self.hop, device=self.device)))
-        seconds = self.clip_len / float(self.sr)
-        self.rows_per_clip = int(self.roll_fs * seconds)
-        self.plane_sub = max(1, min(self.n, int(256 * 4.0 / max(seconds, 1e-3))))  # pieces per audio-rate launch
+        self.seconds = self.clip_len / float(self.sr)
+        # every piece is rasterised over the clip's duration (end_time = clip seconds), so each owns exactly
+        # rows_per_clip rows and piece i of the batch sits at h_roll[i * rows_per_clip : (i + 1) * rows_per_clip]
+        self.rows_per_clip = int(self.roll_fs * self.seconds)
+        self.plane_sub = max(1, min(self.n, int(256 * 4.0 / max(self.seconds, 1e-3))))  # pieces per audio-rate launch
         # pinned host outputs
         self.h_mel = torch.empty(self.n * n_mels * self.frames, dtype=torch.float32).pin_memory()
         self.h_wave = torch.empty(self.n * self.wave_len, dtype=torch.float32).pin_memory()
         self.h_roll = torch.empty((self.n * self.rows_per_clip, 128), dtype=torch.uint8).pin_memory()
         self.h_onoff = torch.empty((self.n * self.rows_per_clip, 128), dtype=torch.int8).pin_memory()
-        self.h_planes = (torch.empty(2 * self.plane_sub * n_keys * self.clip_len, dtype=torch.int8).pin_memory()
-                         if planes_to_host else None)
+        # audio-rate planes are 15.5 MB per 4 s clip: the host side is a staging ring with ONE slot per stream (copies on
+        # a stream are ordered, so a slot is never written by two streams); a consumer drains a slot before the stream's
+        # next sub-batch lands.  This measures the transfer; it does not retain 250 GB of planes.
+        self.h_planes = ([torch.empty(2 * self.plane_sub * n_keys * self.clip_len, dtype=torch.int8).pin_memory()
+                          for _ in range(self.n_streams)] if planes_to_host else None)
         self.d2h_roll_bytes = 0
-        self._notes_key = None
+        self.h2d_note_bytes = 0
+        self._note_cap = 0
 
-    def _prepare_notes(self, notes):
-        """notes = (pitch, velocity, start, end, note_offsets) host arrays for the n pieces -> pinned per-chunk slices."""
-        if self._notes_key is notes:
-            return
+    def _stage_notes(self, notes):
+        """notes = (pitch, velocity, start, end, note_offsets) host arrays for the n pieces -> pinned staging buffers.
+        Runs on EVERY call (it is part of the host -> device path): four memcpys into page-locked memory plus the
+        per-chunk offset arrays."""
         pitch, vel, start, end, off = notes
         off = np.asarray(off, dtype=np.int64)
-        pins = [torch.from_numpy(np.ascontiguousarray(a[:int(off[self.n])])).pin_memory() for a in (pitch, vel, start, end)]
+        total = int(off[self.n])
+        if total > self._note_cap:
+            cap = int(total * 1.25) + 1024
+            self._pins = [torch.empty(cap, dtype=dt).pin_memory() for dt in (torch.int32, torch.int32, torch.float64, torch.float64)]
+            self._pin_off = torch.empty(self.n + len(self.chunks) + 1, dtype=torch.int64).pin_memory()
+            self._note_cap = cap
+        for t, a in zip(self._pins, (pitch, vel, start, end)):
+            np.copyto(t.numpy()[:total], np.asarray(a)[:total], casting="same_kind")
+        o = 0
         for ch in self.chunks:
             a0, a1 = ch["a0"], ch["a1"]
             n0, n1 = int(off[a0]), int(off[a1])
-            ch["notes"] = [t[n0:n1] for t in pins]
-            ch["noff"] = torch.from_numpy(np.ascontiguousarray(off[a0:a1 + 1] - off[a0])).pin_memory()
-            e = np.asarray(end, dtype=np.float64)
-            ch["h_max_end"] = np.array([e[off[i]:off[i + 1]].max() if off[i + 1] > off[i] else 0.0 for i in range(a0, a1)])
-        self.h2d_note_bytes = sum(t.numel() * t.element_size() for t in pins) + (self.n + 1) * 8
-        self._notes_key = notes
+            ch["notes"] = [t[n0:n1] for t in self._pins]
+            dst = self._pin_off[o:o + (a1 - a0 + 1)]
+            np.subtract(off[a0:a1 + 1], off[a0], out=dst.numpy())
+            ch["noff"] = dst
+            o += a1 - a0 + 1
+        self.h2d_note_bytes = total * (4 + 4 + 8 + 8) + (self.n + len(self.chunks)) * 8
 
     def run(self, h_audio, h_S, notes, seed=7):
         """h_audio: pinned float32 [n * clip_len]; h_S: pinned float32 frame-major magnitudes [n * frames * 1025];
-        notes: host SoA arrays.  Results land in self.h_mel / h_wave / h_roll / h_onoff (and h_planes)."""
-        self._prepare_notes(notes)
+        notes: host SoA arrays.  Results land in self.h_mel / h_wave / h_roll / h_onoff (and the h_planes ring)."""
+        self._stage_notes(notes)
         dev, K = self.device, F.N_BINS
         main = torch.cuda.current_stream()
         for s_ in self.streams:
@@ -83,26 +97,28 @@ class HostPipeline:
         self.d2h_roll_bytes = 0
         for ci, ch in enumerate(self.chunks):
             a0, a1, m = ch["a0"], ch["a1"], ch["m"]
-            with torch.cuda.stream(self.streams[ci % self.n_streams]):
+            si = ci % self.n_streams
+            with torch.cuda.stream(self.streams[si]):
                 a = h_audio[a0 * self.clip_len:a1 * self.clip_len].to(dev, non_blocking=True)
                 mel = F.melspectrogram_batch(a, ch["batch"], self.plan, log1p=True, layout=F.BIN_MAJOR)
                 self.h_mel[a0 * self.n_mels * self.frames:a1 * self.n_mels * self.frames].copy_(mel, non_blocking=True)
-                nb = PR.NoteBatch.from_host_tensors(*ch["notes"], ch["noff"], ch["h_max_end"], device=dev)
+                nb = PR.NoteBatch.from_host_tensors(*ch["notes"], ch["noff"], np.full(m, self.seconds), device=dev)
                 roll, onoff, row_off, _ = PR.rasterize(nb, self.roll_fs)
-                rows = min(roll.shape[0], m * self.rows_per_clip)
+                rows = m * self.rows_per_clip
+                assert roll.shape[0] == rows
                 r0 = a0 * self.rows_per_clip
-                self.h_roll[r0:r0 + rows].copy_(roll[:rows], non_blocking=True)
-                self.h_onoff[r0:r0 + rows].copy_(onoff[:rows], non_blocking=True)
+                self.h_roll[r0:r0 + rows].copy_(roll, non_blocking=True)
+                self.h_onoff[r0:r0 + rows].copy_(onoff, non_blocking=True)
                 self.d2h_roll_bytes += 2 * rows * 128
                 for s in range(0, m, self.plane_sub):
                     e = min(m, s + self.plane_sub)
                     ro = row_off[s:e + 1]
-                    ua, _ = PR.upsample(roll, ro, self.clip_len, self.roll_fs, self.sr, self.pitch_lo, self.n_keys, torch.int8)
-                    ub, _ = PR.upsample(onoff, ro, self.clip_len, self.roll_fs, self.sr, self.pitch_lo, self.n_keys, torch.int8)
+                    ua, ub = PR.upsample_pair(roll, onoff, ro, self.clip_len, self.roll_fs, self.sr, self.pitch_lo,
+                                              self.n_keys, torch.int8)
                     if self.planes_to_host:
                         k = (e - s) * self.n_keys * self.clip_len
-                        self.h_planes[:k].copy_(ua, non_blocking=True)
-                        self.h_planes[k:2 * k].copy_(ub, non_blocking=True)
+                        self.h_planes[si][:k].copy_(ua, non_blocking=True)
+                        self.h_planes[si][k:2 * k].copy_(ub, non_blocking=True)
                 Sd = h_S[a0 * self.frames * K:a1 * self.frames * K].to(dev, non_blocking=True)
                 y = F.griffinlim_batch(Sd, ch["gl_batch"], n_iter=self.gl_iters, momentum=0.99, init="random", seed=seed,
                                        layout=F.FRAME_MAJOR)
@@ -113,7 +129,7 @@ class HostPipeline:
         return self
 
     def bytes_per_run(self):
-        h2d = self.n * self.clip_len * 4 + self.n * self.frames * F.N_BINS * 4 + getattr(self, "h2d_note_bytes", 0)
+        h2d = self.n * self.clip_len * 4 + self.n * self.frames * F.N_BINS * 4 + self.h2d_note_bytes
         d2h = self.h_mel.numel() * 4 + self.h_wave.numel() * 4 + self.d2h_roll_bytes
         if self.planes_to_host:
             d2h += 2 * self.n * self.n_keys * self.clip_len

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib, audio_io, features, pianoroll as _pr
-from .midi import read_midi, read_midi_notes
+from .midi import read_midi, read_midi_file, read_midi_notes
 
 
 class hyperparams(object):
@@ -134,8 +134,9 @@ def load_midi(data_dir, song_id, ext='mixcraft', debug=False):
         raise ValueError("couldnt find midi track!")
     elif len(midi_file) > 1:
         raise ValueError("multiple files picked up, issue:", midi_file)
-    pitch, velocity, start, end, cc64, end_time = read_midi(midi_file[0])
-    pianoroll, onoff = notes_to_pianoroll(pitch, velocity, start, end, cc64=cc64, end_time=end_time)
+    # PrettyMIDI(file).get_piano_roll(fs=hp.wps).T with every instrument's own pedal / bends, then binarise + on/off
+    roll, oo, _, _ = _pr.midi_to_pianoroll(read_midi_file(midi_file[0]), hp.wps)
+    pianoroll, onoff = roll.to(torch.float64).cpu().numpy(), oo.to(torch.float64).cpu().numpy()
     if debug is True:
         print("length of pianoroll: ", pianoroll.shape)
         print("midi files picked up:", midi_file)
@@ -146,7 +147,7 @@ def get_data(data_dir, dataset_outpath, data_type, debug=False, piano_scores=Non
     """preprocess.py:163-200 with the HDF5 file replaced by a shard directory ``{dataset_outpath}_{data_type}``
     (dataset.ShardManager mirrors io_manager.h5pyManager).  ``piano_scores`` / ``styles`` default to ``hp``'s."""
     from .dataset import ShardManager
-    data_manager = ShardManager(f"{dataset_outpath}_{data_type}")
+    data_manager = ShardManager(f"{dataset_outpath}_{data_type}", mode="w")   # h5py.File(outfile, 'w') truncates too
     for song_id in (hp.piano_scores[data_type] if piano_scores is None else piano_scores):
         pianoroll, onoff = load_midi(data_dir, song_id, debug=debug)
         num_chunks = get_num_song_chunks(pianoroll)

@@ -11,12 +11,13 @@ pretty_midi semantics followed (pretty_midi is absent from this image):
   Instrument.get_piano_roll(fs): ``roll = zeros((128, int(fs * end_time)))`` with end_time the
   latest note end; for each note ``roll[pitch, int(start*fs):int(end*fs)] += velocity`` (float64
   products truncated toward zero by ``int``); PrettyMIDI.get_piano_roll sums the instruments
-  into the widest roll.  CC64 sustain and pitch bends are outside the GPU contract.
+  into the widest roll; CC64 sustain spans keep a running maximum; pitch bends shift / interpolate rows
+  (``instrument_piano_roll`` / ``prettymidi_piano_roll`` restate those statement by statement).
 """
 import numpy as np
 
 __all__ = ["get_piano_roll", "binarize_and_onoff", "onoff_reference_loop", "upsample_to_audio_rate",
-           "process_pianoroll_into_chunks", "get_num_song_chunks"]
+           "process_pianoroll_into_chunks", "get_num_song_chunks", "instrument_piano_roll", "prettymidi_piano_roll"]
 
 
 def get_piano_roll(pitch, velocity, start, end, fs, end_time=None, cc64=None, pedal_threshold=64):
@@ -45,6 +46,69 @@ def get_piano_roll(pitch, velocity, start, end, fs, end_time=None, cc64=None, pe
                 roll[:, time_pedal_on:time_now] = np.maximum.accumulate(subpr, axis=1)
                 is_pedal_on = False
     return roll
+
+
+def instrument_piano_roll(inst, fs=100, pedal_threshold=64):
+    """pretty_midi 0.2.9 ``Instrument.get_piano_roll(fs, times=None, pedal_threshold)`` restated statement by
+    statement: notes, CC64 running maximum, pitch bends (integer row shift + linear interpolation by the fractional
+    part).  ``inst`` exposes is_drum, pitch / velocity / start / end (parallel sequences), control_changes
+    [(number, value, time)] and pitch_bends [(pitch, time)] in file order."""
+    if len(inst.pitch) == 0:
+        return np.array([[]] * 128)
+    events = [float(e) for e in inst.end] + [t for _, t in inst.pitch_bends] + [t for _, _, t in inst.control_changes]
+    end_time = max(events)
+    piano_roll = np.zeros((128, int(fs * end_time)))
+    if inst.is_drum:
+        return piano_roll
+    for p, v, s, e in zip(inst.pitch, inst.velocity, inst.start, inst.end):
+        piano_roll[int(p), int(float(s) * fs):int(float(e) * fs)] += int(v)
+    if pedal_threshold is not None:
+        time_pedal_on, is_pedal_on = 0, False
+        for num, val, t in inst.control_changes:
+            if num != 64:
+                continue
+            time_now = int(t * fs)
+            is_current_pedal_on = val >= pedal_threshold
+            if not is_pedal_on and is_current_pedal_on:
+                time_pedal_on, is_pedal_on = time_now, True
+            elif is_pedal_on and not is_current_pedal_on:
+                subpr = piano_roll[:, time_pedal_on:time_now]
+                piano_roll[:, time_pedal_on:time_now] = np.maximum.accumulate(subpr, axis=1)
+                is_pedal_on = False
+    ordered_bends = sorted(inst.pitch_bends, key=lambda bend: bend[1])
+    for (start_pitch_raw, start_t), (_, end_t) in zip(ordered_bends, ordered_bends[1:] + [(0, end_time)]):
+        if np.abs(start_pitch_raw) < 1:
+            continue
+        start_pitch = 2.0 * start_pitch_raw / 8192.0            # pitch_bend_to_semitones, semitone_range=2
+        bend_int = int(np.sign(start_pitch) * np.floor(np.abs(start_pitch)))
+        bend_decimal = np.abs(start_pitch - bend_int)
+        bend_range = np.r_[int(start_t * fs):int(end_t * fs)]
+        bent_roll = np.zeros(piano_roll[:, bend_range].shape)
+        if start_pitch_raw >= 0:
+            if bend_int != 0:
+                bent_roll[bend_int:] = piano_roll[:-bend_int, bend_range]
+            else:
+                bent_roll = piano_roll[:, bend_range]
+            bent_roll[1:] = ((1 - bend_decimal) * bent_roll[1:] + bend_decimal * bent_roll[:-1])
+        else:
+            if bend_int != 0:
+                bent_roll[:bend_int] = piano_roll[-bend_int:, bend_range]
+            else:
+                bent_roll = piano_roll[:, bend_range]
+            bent_roll[:-1] = ((1 - bend_decimal) * bent_roll[:-1] + bend_decimal * bent_roll[1:])
+        piano_roll[:, bend_range] = bent_roll
+    return piano_roll
+
+
+def prettymidi_piano_roll(instruments, fs=100, pedal_threshold=64):
+    """pretty_midi 0.2.9 ``PrettyMIDI.get_piano_roll(fs)``: per-instrument rolls summed into the widest one."""
+    if len(instruments) == 0:
+        return np.zeros((128, 0))
+    piano_rolls = [instrument_piano_roll(i, fs, pedal_threshold) for i in instruments]
+    piano_roll = np.zeros((128, np.max([p.shape[1] for p in piano_rolls])))
+    for roll in piano_rolls:
+        piano_roll[:, :roll.shape[1]] += roll
+    return piano_roll
 
 
 def onoff_reference_loop(pianoroll):

@@ -318,6 +318,63 @@ def test_pianoroll_sustain_pedal(pkg, gpu, tmp_path):
     assert got_r.sum() > opp.midi_notes_to_pianoroll(rp, rv, rs, re_)[0].sum()  # the pedal really sustained something
 
 
+def _random_midi_file(path, seed, n_tracks=3):
+    """Multi-track file: pitched instruments on distinct channels with their own pedal and pitch-bend streams, a program
+    change mid-track, a drum track, and a channel that only sends control changes."""
+    from ml_music_style_transfer_b200 import midi, synth
+    rng = np.random.default_rng(seed)
+    tracks = []
+    for tr in range(n_tracks):
+        ch = tr
+        p, v, s, e = synth.midi_piece(500 + 10 * seed + tr, seconds=5.0 + tr, notes_per_second=6.0)
+        ev = [('note', ch, int(a), int(b), float(c), float(d)) for a, b, c, d in zip(p, v, s, e)]
+        for t in np.sort(rng.uniform(0, 6.5 + tr, 10)):
+            ev.append(('cc', ch, 64, int(rng.choice([0, 30, 64, 90, 127])), float(t)))
+        for t in np.sort(rng.uniform(0, 6.0 + tr, 12)):
+            ev.append(('bend', ch, int(rng.choice([0, 0, 1, -1, 700, -700, 2048, 4096, -4096, 5000, -6000, 8191, -8192])), float(t)))
+        ev.append(('cc', ch, 7, 100, 0.0))
+        if tr == 1:
+            ev.append(('program', ch, 40, 2.5))          # notes closed after 2.5 s land in a second instrument
+        tracks.append(ev)
+    tracks.append([('note', 9, 36, 120, 0.0, 9.5), ('note', 9, 38, 90, 1.0, 1.2)])   # drums: zeros, but 9.5 s wide
+    tracks[0].append(('cc', 12, 64, 127, 30.0))                                         # note-less channel: ignored
+    midi.write_midi_tracks(path, tracks)
+
+
+@pytest.mark.parametrize("fs", [172, 250])
+def test_midi_full_get_piano_roll(pkg, gpu, tmp_path, fs):
+    """PrettyMIDI(file).get_piano_roll(fs) semantics on whole files: per-instrument CC64 sustain, pitch bends
+    (float64, NumPy's rounding sequence), drums, instrument sum -- bit exact against the oracle, two files in one batch."""
+    from ml_music_style_transfer_b200 import midi
+    P = pkg.pianoroll
+    files = []
+    for i in range(2):
+        path = str(tmp_path / f"{2308 + i}_multi_mixcraft.mid")
+        _random_midi_file(path, i)
+        files.append(midi.read_midi_file(path))
+    assert len(files[0].instruments) == 5 and any(i.is_drum for i in files[0].instruments)
+    roll, onoff, row_off, vs = P.midi_to_pianoroll(files, fs, want_f64=True)
+    ro = row_off.cpu().numpy()
+    bent = False
+    for i, mf in enumerate(files):
+        ref_v = opr.prettymidi_piano_roll(mf.instruments, fs)
+        ref_r, ref_o = opr.binarize_and_onoff(ref_v)
+        assert ro[i + 1] - ro[i] == ref_v.shape[1] == int(fs * 9.5)
+        assert np.array_equal(vs[ro[i]:ro[i + 1]].cpu().numpy().T, ref_v)          # float64 values, bit for bit
+        assert np.array_equal(roll[ro[i]:ro[i + 1]].cpu().numpy(), ref_r)
+        assert np.array_equal(onoff[ro[i]:ro[i + 1]].cpu().numpy(), ref_o)
+        bent |= bool((ref_v != np.floor(ref_v)).any())
+        # per-instrument pedals matter: merging all channels into one instrument gives a different roll
+        rp, rv, rs, re_, cc, end_time = midi.read_midi(str(tmp_path / f"{2308 + i}_multi_mixcraft.mid"))
+        merged = opr.get_piano_roll(rp, rv, rs, re_, fs, end_time=end_time, cc64=cc)
+        assert merged.shape == ref_v.shape and not np.array_equal(merged != 0, ref_v != 0)
+    assert bent                                                                      # fractional bends were exercised
+    # the drop-in reads the same file through the same path (fs = hp.wps = 172)
+    got_r, got_o = pkg.preprocess.load_midi(str(tmp_path), 2308)
+    ref_r, ref_o = opr.binarize_and_onoff(opr.prettymidi_piano_roll(files[0].instruments, 172))
+    assert got_r.dtype == np.float64 and np.array_equal(got_r, ref_r) and np.array_equal(got_o, ref_o)
+
+
 def test_process_pianoroll_into_chunks_dropin(pkg):
     from ml_music_style_transfer_b200 import synth
     p, v, s, e = synth.midi_piece(3, seconds=14.0)
@@ -407,6 +464,19 @@ def test_get_data_end_to_end(pkg, tmp_path):
     assert np.array_equal(X.numpy(), np.concatenate((ra[1], rb[1]), axis=-1).T.astype(np.float32))
     refs = [opp.process_audio_into_chunks(audio[st], st, 1749, n)[1] for st in audio]
     assert min(rel_l2(y.numpy(), r.astype(np.float64)) for r in refs) <= TOL
+    # device-resident dataset: same items (same RNG stream), served from GPU memory without a host hop
+    ds_h = ShardDataset(str(tmp_path / "out_train"), seed=7)
+    ds_d = ShardDataset(str(tmp_path / "out_train"), seed=7, device="cuda:0")
+    assert ds_d.resident and ds_d.pianoroll.is_cuda and ds_d.pianoroll.dtype == torch.int8
+    items_h = [ds_h[i] for i in range(len(ds_h))]
+    ds_d.__init__(str(tmp_path / "out_train"), seed=7, device="cuda:0")   # restart the RNG stream
+    for i, (Xh, Ch, yh) in enumerate(items_h):
+        Xd, Cd, yd = ds_d[i]
+        assert Xd.is_cuda and Xd.shape == (256, 860) and Xd.dtype == torch.float32
+        assert torch.equal(Xd.cpu(), Xh) and torch.equal(Cd.cpu(), Ch) and torch.equal(yd.cpu(), yh)
+    # running get_data again truncates (h5py.File(..., 'w') semantics) instead of duplicating every song
+    mgr2 = pkg.preprocess.get_data(str(tmp_path), str(tmp_path / "out"), "train", piano_scores=[1749], styles=["cuba"])
+    assert mgr2.n_rows("pianoroll") == n and sorted(mgr2.keys()) == ["onoff", "pianoroll", "spec_cuba"]
 
 
 # ---- P4: Griffin-Lim ------------------------------------------------------------------------

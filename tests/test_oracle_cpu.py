@@ -286,6 +286,17 @@ def test_shard_dataset_container(tmp_path):
     assert any(np.array_equal(y.numpy(), np.concatenate(specs[st])[4]) for st in specs)
     with pytest.raises(ValueError):
         m.write_spectrum(np.zeros((1, 1025, 100), dtype=np.float32), "cuba")
+    # modes: 'a' re-opens and appends, an explicit dtype must agree with the container, 'w' truncates like h5py 'w'
+    m2 = ShardManager(str(tmp_path / "ds_train"))
+    assert m2.dtype == "native" and m2.n_rows("pianoroll") == 5
+    with pytest.raises(ValueError):
+        ShardManager(str(tmp_path / "ds_train"), dtype="float64")
+    with pytest.raises(IOError):
+        ShardManager(str(tmp_path / "ds_train"), mode="r").write_pianoroll(rolls[0], oos[0])
+    m3 = ShardManager(str(tmp_path / "ds_train"), dtype="float64", mode="w")
+    assert m3.keys() == [] and not os.path.exists(str(tmp_path / "ds_train" / "pianoroll" / "00000.npy"))
+    m3.write_pianoroll(rolls[0], oos[0])
+    assert m3.n_rows("pianoroll") == 3 and m3.read("pianoroll").dtype == np.float64
 
 
 def test_shard_ranges_partition():
