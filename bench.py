@@ -173,8 +173,7 @@ def run_ours(args):
         for s in range(0, n_clips, roll_sub):
             e = min(n_clips, s + roll_sub)
             ro = row_off[s:e + 1]
-            a, _ = PR.upsample(roll, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
-            b, _ = PR.upsample(onoff, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
+            a, b, _ = PR.upsample_pair(roll, onoff, ro, CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
             outs = (a, b)
         return outs
 

@@ -165,6 +165,12 @@ int mst_pianoroll_chunks(const void* d_plane, int64_t n_rows, int num_chunks, in
 int mst_pianoroll_upsample(const void* d_plane, const int64_t* d_row_offsets, const int64_t* d_sample_offsets,
                            int n_pieces, int64_t total_samples, int fs, int sr, int pitch_lo, int n_keys,
                            int out_dtype, void* d_out, mst_stream_t stream);
+/* The same for the roll and its on/off map in ONE launch (the two planes that condition the model, README.md:19-20,27):
+ * the index arithmetic is shared.  d_out_roll / d_out_onoff must agree in alignment modulo 16 bytes. */
+int mst_pianoroll_upsample_pair(const void* d_roll, const void* d_onoff, const int64_t* d_row_offsets,
+                                const int64_t* d_sample_offsets, int n_pieces, int64_t total_samples, int fs, int sr,
+                                int pitch_lo, int n_keys, int out_dtype, void* d_out_roll, void* d_out_onoff,
+                                mst_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * P4: Griffin-Lim phase reconstruction (fast Griffin-Lim, momentum; momentum=0 is the classic

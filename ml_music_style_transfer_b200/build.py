@@ -96,9 +96,25 @@ def build_ops(force=False):
     return LIB_OPS
 
 
+def build_tools(force=False):
+    """tools/ubench: standalone microbenchmarks (write bandwidth ceiling, FFMA2 issue rate) quoted in DESIGN.md."""
+    src = os.path.join(HERE, "..", "tools", "ubench.cu")
+    out = os.path.join(HERE, "..", "tools", "ubench")
+    if not os.path.exists(src):
+        return None
+    stamp = _digest([src])
+    if not force and not _stale(out, stamp):
+        return out
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+                           "-o", out, src])
+    _write_stamp(out, stamp)
+    return out
+
+
 def build_all(force=False, verbose=False):
     build_cuda(force=force, verbose=verbose)
     build_ops(force=force)
+    build_tools(force=force)
     return LIB_CUDA, LIB_OPS
 
 

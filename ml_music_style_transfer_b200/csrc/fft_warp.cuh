@@ -41,8 +41,51 @@ struct Tw32 {
   }
 };
 
+// ---- packed fp32x2 arithmetic (sm_100: PTX fma/add/mul.rn.f32x2 -> SASS FFMA2 / FADD2 / FMUL2) ------------------------
+// One instruction does the same IEEE operation on both halves of a 64-bit register pair, i.e. on (re, im) of a float2.
+// ptxas folds half swaps, per-half negation, scalar broadcast and immediates into operand modifiers
+// (R4.F32x2.LO_HI.NP, R0.F32, 0.92387...), so a complex radix-2 butterfly is 3 issue slots instead of 6 and every
+// result is bit-identical to the scalar formulation.  The FFT kernels are issue-bound, not FMA-pipe-bound.
+#ifndef MST_PACKED
+#define MST_PACKED 1
+#endif
+#if MST_PACKED
+__device__ __forceinline__ unsigned long long pk_pack(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 pk_unpack(unsigned long long r) {
+  float2 a;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+  return a;
+}
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b)), "l"(pk_pack(c)));
+  return pk_unpack(d);
+}
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b)));
+  return pk_unpack(d);
+}
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b)));
+  return pk_unpack(d);
+}
+#else
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#endif
+__device__ __forceinline__ float2 pk_bcast(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 pk_neg(float2 a) { return make_float2(-a.x, -a.y); }
+
+// a * b (complex):  (a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x) as  a.x * b + a.y * (-b.y, b.x)
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+  return pk_fma(pk_bcast(a.x), b, pk_mul(pk_bcast(a.y), make_float2(-b.y, b.x)));
 }
 
 // One radix-2 decimation-in-time butterfly with the compile-time twiddle w = W_32^Q (forward) / conj (inverse):
@@ -53,34 +96,29 @@ template <int SIGN, int Q>
 __device__ __forceinline__ void bfly(float2& a, float2& b) {
   if (Q == 0) {
     const float2 t = b;
-    b = make_float2(a.x - t.x, a.y - t.y);
-    a = make_float2(a.x + t.x, a.y + t.y);
+    b = pk_add(a, pk_neg(t));
+    a = pk_add(a, t);
   } else if (Q == 8) {  // w = SIGN * i:  t = SIGN * (-b.y, b.x)
-    const float tx = SIGN < 0 ? b.y : -b.y, ty = SIGN < 0 ? -b.x : b.x;
-    b = make_float2(a.x - tx, a.y - ty);
-    a = make_float2(a.x + tx, a.y + ty);
+    const float2 t = SIGN < 0 ? make_float2(b.y, -b.x) : make_float2(-b.y, b.x);
+    b = pk_add(a, pk_neg(t));
+    a = pk_add(a, t);
   } else if (Q == 4 || Q == 12) {
     // Q=4:  w = c*(1 + SIGN*i)  -> t = c*(b.x - SIGN*b.y, b.y + SIGN*b.x)
     // Q=12: w = c*(-1 + SIGN*i) -> t = c*(-b.x - SIGN*b.y, -b.y + SIGN*b.x)
     constexpr float c = MST_C4;
-    float ux, uy;
-    if (Q == 4) {
-      ux = SIGN < 0 ? b.x + b.y : b.x - b.y;
-      uy = SIGN < 0 ? b.y - b.x : b.y + b.x;
-    } else {
-      ux = SIGN < 0 ? b.y - b.x : -(b.x + b.y);
-      uy = SIGN < 0 ? -(b.x + b.y) : b.x - b.y;
-    }
-    const float ax = fmaf(c, ux, a.x), ay = fmaf(c, uy, a.y);
-    b = make_float2(fmaf(2.0f, a.x, -ax), fmaf(2.0f, a.y, -ay));
-    a = make_float2(ax, ay);
+    const float2 rot = SIGN < 0 ? make_float2(b.y, -b.x) : make_float2(-b.y, b.x);  // SIGN * i * b
+    const float2 u = pk_add(Q == 4 ? b : pk_neg(b), rot);
+    const float2 a2 = pk_fma(pk_bcast(c), u, a);
+    b = pk_fma(pk_bcast(2.0f), a, pk_neg(a2));
+    a = a2;
   } else {
     constexpr float wr = Tw32<Q>::cosv();
     constexpr float wi = SIGN * Tw32<Q>::sinv();
-    const float ax = fmaf(wr, b.x, fmaf(-wi, b.y, a.x));
-    const float ay = fmaf(wr, b.y, fmaf(wi, b.x, a.y));
-    b = make_float2(fmaf(2.0f, a.x, -ax), fmaf(2.0f, a.y, -ay));
-    a = make_float2(ax, ay);
+    // a' = a + w*b = a + wi*(-b.y, b.x) + wr*b ;  b' = 2a - a'
+    const float2 u = pk_fma(pk_bcast(wi), make_float2(-b.y, b.x), a);
+    const float2 a2 = pk_fma(pk_bcast(wr), b, u);
+    b = pk_fma(pk_bcast(2.0f), a, pk_neg(a2));
+    a = a2;
   }
 }
 
@@ -180,11 +218,11 @@ __device__ __forceinline__ int mirror_bin(int lane, int kb, int j) { return j < 
 // caller for the inverse direction).  Returns out_k = 0.5*(z + conj p) + w*(z - conj p) and
 // out_m = conj(0.5*(z + conj p) - w*(z - conj p)).
 __device__ __forceinline__ void pair_butterfly(float2 z, float2 p, float2 w, float2& out_k, float2& out_m) {
-  const float sx = z.x + p.x, sy = z.y - p.y;
-  const float dx = z.x - p.x, dy = z.y + p.y;
-  const float tx = fmaf(w.x, dx, -w.y * dy), ty = fmaf(w.x, dy, w.y * dx);
-  out_k = make_float2(fmaf(0.5f, sx, tx), fmaf(0.5f, sy, ty));
-  out_m = make_float2(fmaf(0.5f, sx, -tx), fmaf(-0.5f, sy, ty));
+  const float2 s = pk_add(z, make_float2(p.x, -p.y));   // z + conj p
+  const float2 d = pk_add(z, make_float2(-p.x, p.y));   // z - conj p
+  const float2 t = pk_fma(pk_bcast(w.x), d, pk_mul(pk_bcast(w.y), make_float2(-d.y, d.x)));  // w * d
+  out_k = pk_fma(pk_bcast(0.5f), s, t);
+  out_m = pk_fma(make_float2(0.5f, -0.5f), s, make_float2(-t.x, t.y));
 }
 
 // Forward real FFT of a 2048-sample frame held as z[m] = x[2m] + i*x[2m+1], m = 32*r + lane in v[r].

@@ -11,7 +11,7 @@
 // rotating overlap-add accumulators (read y_{j-1}, accumulate y_j, zero the one the next launch accumulates into).
 // The phase itself never touches HBM: it is recomputed from rebuilt_j and rebuilt_{j-1} in registers.
 //
-// Overlap-add: the 8 frames of a tile are summed in shared memory in frame order, hop-block by hop-block.  Blocks that
+// Overlap-add: the frames of a tile (kWarpsPerCta = 8) are summed in shared memory in frame order, hop-block by hop-block.  Blocks that
 // only this tile touches are written with plain 128-bit stores; the blocks a tile shares with its neighbour go to the
 // global accumulator as 128-bit vector reductions (red.global.add.v4.f32).  At most two tiles touch a shared sample
 // (hop >= 256) and the shared region was zeroed one launch earlier, so the result does not depend on the order the two
@@ -73,9 +73,7 @@ __device__ __forceinline__ void synthesize_frame(float2 (&y)[32], float2 mid, fl
   const float2* w2 = reinterpret_cast<const float2*>(s_wsyn);
 #pragma unroll
   for (int r = 0; r < 32; ++r) {
-    const float2 w = w2[lane + 32 * r];
-    const float2 z = v[br5(r)];
-    scratch[lane + 32 * r] = make_float2(z.x * w.x, z.y * w.y);  // samples 2m, 2m+1
+    scratch[lane + 32 * r] = pk_mul(v[br5(r)], w2[lane + 32 * r]);  // samples 2m, 2m+1
   }
 }
 
@@ -108,7 +106,9 @@ __device__ __forceinline__ void ola_blocks(const float* s_slots, int nvalid, int
       const int f = b - r;
       if (f >= 0 && f < nvalid) {
         const float4 v = *reinterpret_cast<const float4*>(sp + f * kSlot + (r << hop_shift));
-        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        const float2 lo = pk_add(make_float2(sum.x, sum.y), make_float2(v.x, v.y));
+        const float2 hi = pk_add(make_float2(sum.z, sum.w), make_float2(v.z, v.w));
+        sum = make_float4(lo.x, lo.y, hi.x, hi.y);
       }
     }
     float* p = dst + (b << hop_shift) + j;
@@ -267,8 +267,7 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
             const float2 a = COHERENT ? __ldcg(a2 + 32 * r) : a2[32 * r];
-            const float2 w = w2[32 * r];
-            v[r] = make_float2(a.x * w.x, a.y * w.y);
+            v[r] = pk_mul(a, w2[32 * r]);
           }
         } else {
           // edge frame (rare): stage through this warp's scratch with a compact loop
@@ -325,18 +324,16 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
             float2 tp = make_float2(0.0f, 0.0f);
             if (!FIRST) tp = scratch[mirror_bin(lane, kb, j)];
             if (!P.last_iter) (j < 16 ? TA : TB)[32 * j] = y[j];
-            const float ax = fmaf(-P.alpha, tp.x, y[j].x), ay = fmaf(-P.alpha, tp.y, y[j].y);
-            const float sc = sm[i] * unit_scale(ax, ay);
-            y[j] = make_float2(sc * ax, sc * ay);
+            const float2 a = pk_fma(pk_bcast(-P.alpha), tp, y[j]);
+            y[j] = pk_mul(pk_bcast(sm[i] * unit_scale(a.x, a.y)), a);
           }
         }
         if (lane == 0) {
           float2 tp = make_float2(0.0f, 0.0f);
           if (!FIRST) tp = scratch[512];
           if (!P.last_iter) trow[512] = mid;
-          const float ax = fmaf(-P.alpha, tp.x, mid.x), ay = fmaf(-P.alpha, tp.y, mid.y);
-          const float sc = ld_stream(Srow + 512) * unit_scale(ax, ay);
-          mid = make_float2(sc * ax, sc * ay);
+          const float2 a = pk_fma(pk_bcast(-P.alpha), tp, mid);
+          mid = pk_mul(pk_bcast(ld_stream(Srow + 512) * unit_scale(a.x, a.y)), a);
         }
         __syncwarp();  // everyone is done reading the staged previous iterate before the inverse FFT reuses the tile
       }

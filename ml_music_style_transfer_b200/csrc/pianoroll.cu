@@ -193,50 +193,86 @@ __global__ void chunks_kernel(const int8_t* __restrict__ plane, int64_t n_rows, 
   }
 }
 
-// Audio-rate hold-replication: out[k][n] = plane[(n*fs)/sr][pitch_lo + k].  One warp owns a chunk of 32 x kUpVec 16-byte
-// vectors of one key row (4096 int8 / 1024 float samples): fully coalesced 128-bit stores, ONE 64-bit division per
-// thread per chunk (the column / remainder pair is then advanced incrementally), and a branch-free split of each vector
-// at its (single) column crossing: the number of samples left in the current column comes from a multiply-high by a
-// precomputed reciprocal of fs.  Rows need not start 16-byte aligned: scalar head / tail elements are written by the
-// warp that owns chunk 0.  If one vector could span more than two columns (fs * EPV > sr) a generic loop is used.
+// Audio-rate hold-replication: out[k][n] = plane[(n*fs)/sr][pitch_lo + k], for ONE or TWO planes (roll + on/off) per
+// launch so that the index arithmetic is done once.  One warp owns a chunk of 32 x kUpVec 16-byte vectors of one key row
+// (4096 int8 / 1024 float samples): fully coalesced 128-bit stores.  The (few) roll columns a chunk can touch are fetched
+// once, one or two bytes per lane and plane, and every vector's current / next column value then comes from a warp
+// shuffle -- no dependent global load inside the store loop.  A piano roll is mostly runs: when all staged columns of a
+// chunk hold the same value (a held or a silent key -- the common case) the chunk is eight plain vector stores of that
+// value, no per-vector arithmetic at all; otherwise the column / remainder pair is advanced incrementally (ONE division
+// per chunk) and each vector is split at its single column crossing with a byte mask (the number of samples left in
+// the current column comes from a multiply-high by a precomputed reciprocal of fs).  Rows need not start 16-byte
+// aligned: scalar head / tail elements are written by the warp that owns chunk 0.  If one vector could span more than
+// two columns (fs * EPV > sr), or a chunk more than 62 columns, a generic loop is used.
 constexpr int kUpVec = 8;  // vectors per lane per chunk
 
-template <typename OUT>
-__device__ __forceinline__ void make_vector(OUT (&vals)[16 / sizeof(OUT)], int8_t cur, int8_t nxt, int e_cross) {
-  constexpr int EPV = 16 / sizeof(OUT);
-  if (sizeof(OUT) == 1) {
-    const unsigned c4 = (unsigned)(uint8_t)cur * 0x01010101u, n4 = (unsigned)(uint8_t)nxt * 0x01010101u;
-    unsigned* w = reinterpret_cast<unsigned*>(vals);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = e_cross - 4 * i;  // bytes of this word that still belong to the current column
-      const unsigned m = k >= 4 ? 0u : (k <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * k)));
-      w[i] = (c4 & ~m) | (n4 & m);
-    }
-  } else {
-#pragma unroll
-    for (int e = 0; e < EPV; ++e) vals[e] = (OUT)(e < e_cross ? cur : nxt);
-  }
+__device__ __forceinline__ unsigned shl_clamp(unsigned x, unsigned n) {  // PTX shl: shift amounts >= 32 give 0
+  unsigned r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+  return r;
 }
 
 template <typename OUT>
-__global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict__ plane, const int64_t* __restrict__ row_off,
-                                                       const int64_t* __restrict__ samp_off, int n_pieces, int fs, int sr,
-                                                       int pitch_lo, int n_keys, OUT* __restrict__ out) {
+__device__ __forceinline__ uint4 make_vector(int8_t cur, int8_t nxt, int e_cross) {
+  constexpr int EPV = 16 / sizeof(OUT);
+  uint4 out;
+  if (sizeof(OUT) == 1) {
+    // bytes [0, e_cross) come from cur, the rest from nxt:  w = n4 ^ ((c4 ^ n4) & low_bytes(k)),  k = e_cross - 4*i
+    const unsigned c4 = __byte_perm((unsigned)(uint8_t)cur, 0u, 0x0000), n4 = __byte_perm((unsigned)(uint8_t)nxt, 0u, 0x0000);
+    const unsigned d = c4 ^ n4;
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int bits = 8 * e_cross - 32 * i;
+      const unsigned m = shl_clamp(1u, (unsigned)(bits < 0 ? 0 : bits)) - 1u;
+      w[i] = n4 ^ (d & m);
+    }
+    out = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    OUT vals[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) vals[e] = (OUT)(e < e_cross ? cur : nxt);
+    out = *reinterpret_cast<const uint4*>(vals);
+  }
+  return out;
+}
+
+template <typename OUT>
+__device__ __forceinline__ uint4 splat_vector(int8_t v) {
+  constexpr int EPV = 16 / sizeof(OUT);
+  if (sizeof(OUT) == 1) {
+    const unsigned c4 = __byte_perm((unsigned)(uint8_t)v, 0u, 0x0000);
+    return make_uint4(c4, c4, c4, c4);
+  }
+  OUT vals[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; ++e) vals[e] = (OUT)v;
+  return *reinterpret_cast<const uint4*>(vals);
+}
+
+template <typename OUT, int NP>
+__global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict__ plane0, const int8_t* __restrict__ plane1,
+                                                       const int64_t* __restrict__ row_off, const int64_t* __restrict__ samp_off,
+                                                       int n_pieces, int fs, int sr, int pitch_lo, int n_keys,
+                                                       OUT* __restrict__ out0, OUT* __restrict__ out1) {
   constexpr int EPV = 16 / sizeof(OUT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_cta = blockDim.x >> 5;
   const bool simple = (int64_t)fs * EPV <= sr;                // at most one column crossing per vector
   const unsigned fs_magic = (unsigned)(0x100000000ull / (unsigned)fs) + 1u;  // exact ceil-div by fs for numerators < 2^32/fs
   const int step_col = (32 * EPV * fs) / sr, step_rem = (32 * EPV * fs) % sr;  // advance of 32 vectors
-  const bool staged = simple && ((int64_t)32 * kUpVec * EPV * fs) / sr + 2 <= 62;  // chunk fits 64 staged columns
+  const int span_cols = (int)(((int64_t)32 * kUpVec * EPV * fs) / sr) + 2;     // columns one chunk can touch (upper bound)
+  const bool staged = simple && span_cols <= 62;                               // they fit the 64 staged columns
+  const int8_t* planes[2] = {plane0, NP > 1 ? plane1 : plane0};
+  OUT* outs[2] = {out0, NP > 1 ? out1 : out0};
   for (int piece = blockIdx.z; piece < n_pieces; piece += gridDim.z) {
     const int64_t r0 = row_off[piece], T = row_off[piece + 1] - r0;
     const int64_t N = samp_off[piece + 1] - samp_off[piece];
     for (int k = blockIdx.y; k < n_keys; k += gridDim.y) {
-      const int8_t* src = plane + r0 * 128 + pitch_lo + k;
-      OUT* row = out + samp_off[piece] * n_keys + (int64_t)k * N;
-      const int64_t mis = (int64_t)(((16 - (reinterpret_cast<uintptr_t>(row) & 15)) & 15) / sizeof(OUT));
+      const int64_t src_off = r0 * 128 + pitch_lo + k;
+      const int64_t row_base = samp_off[piece] * n_keys + (int64_t)k * N;
+      // both outputs share the misalignment of their rows (the host checks that the two bases agree mod 16)
+      const int64_t mis = (int64_t)(((16 - (reinterpret_cast<uintptr_t>(out0 + row_base) & 15)) & 15) / sizeof(OUT));
       const int64_t head = mis < N ? mis : N;
       const int64_t nvec = (N - head) / EPV;
       const int64_t n_chunks = (nvec + 32 * kUpVec - 1) / (32 * kUpVec);
@@ -245,37 +281,66 @@ __global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict_
         if (chunk == 0) {
           // scalar head and tail of the row
           const int64_t tail0 = head + nvec * EPV;
-          for (int64_t n = lane; n < head; n += 32) {
-            const int64_t col = (n * fs) / sr;
-            row[n] = (OUT)(col < T ? src[col * 128] : (int8_t)0);
-          }
-          for (int64_t n = tail0 + lane; n < N; n += 32) {
-            const int64_t col = (n * fs) / sr;
-            row[n] = (OUT)(col < T ? src[col * 128] : (int8_t)0);
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            const int8_t* src = planes[q] + src_off;
+            OUT* row = outs[q] + row_base;
+            for (int64_t n = lane; n < head; n += 32) {
+              const int64_t col = (n * fs) / sr;
+              row[n] = (OUT)(col < T ? src[col * 128] : (int8_t)0);
+            }
+            for (int64_t n = tail0 + lane; n < N; n += 32) {
+              const int64_t col = (n * fs) / sr;
+              row[n] = (OUT)(col < T ? src[col * 128] : (int8_t)0);
+            }
           }
         }
         int64_t v = chunk * (32 * kUpVec) + lane;
-        const int64_t prod = (head + v * EPV) * fs;
-        int64_t col = prod / sr;
-        int rem = (int)(prod - col * sr);
+        // column / remainder of lane 0's first sample by ONE 64-bit division per warp, the other lanes by a 32-bit one
+        const int64_t prod0 = (head + chunk * (32 * kUpVec) * EPV) * fs;
+        const int64_t c0 = prod0 / sr;
+        const unsigned t0 = (unsigned)(prod0 - c0 * sr) + (unsigned)(lane * EPV * fs);
+        int64_t col = c0 + t0 / (unsigned)sr;
+        int rem = (int)(t0 % (unsigned)sr);
         if (staged) {
-          // The chunk spans fewer than 62 roll columns: fetch them once (two bytes per lane) and serve every vector's
-          // current / next column value by warp shuffle -- no dependent global loads inside the store loop.
-          const int64_t c0 = __shfl_sync(0xffffffffu, col, 0);
-          const int8_t b0 = c0 + lane < T ? src[(c0 + lane) * 128] : (int8_t)0;
-          const int8_t b1 = c0 + 32 + lane < T ? src[(c0 + 32 + lane) * 128] : (int8_t)0;
+          int b0 = 0, b1 = 0;   // staged columns c0 + lane and c0 + 32 + lane: byte q = plane q
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            const int8_t* src = planes[q] + src_off;
+            const int x0 = c0 + lane < T ? (int)(uint8_t)src[(c0 + lane) * 128] : 0;
+            const int x1 = c0 + 32 + lane < T ? (int)(uint8_t)src[(c0 + 32 + lane) * 128] : 0;
+            b0 |= x0 << (8 * q);
+            b1 |= x1 << (8 * q);
+          }
+          // uniform chunk: every column this chunk can touch holds the same value(s)
+          const int first = __shfl_sync(0xffffffffu, b0, 0);
+          const bool same = (lane >= span_cols || b0 == first) && (lane + 32 >= span_cols || b1 == first);
+          if (__all_sync(0xffffffffu, same)) {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+              const uint4 val = splat_vector<OUT>((int8_t)((first >> (8 * q)) & 0xff));
+              OUT* dst = outs[q] + row_base + head;
+#pragma unroll
+              for (int u = 0; u < kUpVec; ++u)
+                if (v + 32 * u < nvec) *reinterpret_cast<uint4*>(dst + (v + 32 * u) * EPV) = val;
+            }
+            continue;
+          }
 #pragma unroll
           for (int u = 0; u < kUpVec; ++u) {
             int rel = (int)(col - c0);
             rel = rel < 0 ? 0 : (rel > 62 ? 62 : rel);
-            const int lo0 = __shfl_sync(0xffffffffu, (int)b0, rel & 31), hi0 = __shfl_sync(0xffffffffu, (int)b1, rel & 31);
-            const int lo1 = __shfl_sync(0xffffffffu, (int)b0, (rel + 1) & 31), hi1 = __shfl_sync(0xffffffffu, (int)b1, (rel + 1) & 31);
-            const int8_t cur = (int8_t)(rel < 32 ? lo0 : hi0);
-            const int8_t nxt = (int8_t)(rel + 1 < 32 ? lo1 : hi1);
-            OUT vals[EPV];
+            const int lo0 = __shfl_sync(0xffffffffu, b0, rel & 31), hi0 = __shfl_sync(0xffffffffu, b1, rel & 31);
+            const int lo1 = __shfl_sync(0xffffffffu, b0, (rel + 1) & 31), hi1 = __shfl_sync(0xffffffffu, b1, (rel + 1) & 31);
+            const int cur2 = rel < 32 ? lo0 : hi0;
+            const int nxt2 = rel + 1 < 32 ? lo1 : hi1;
             const int e_cross = (int)__umulhi((unsigned)(sr - rem + fs - 1), fs_magic);
-            make_vector<OUT>(vals, cur, nxt, e_cross);
-            if (v < nvec) *reinterpret_cast<uint4*>(row + head + v * EPV) = *reinterpret_cast<const uint4*>(vals);
+            if (v < nvec) {
+#pragma unroll
+              for (int q = 0; q < NP; ++q)
+                *reinterpret_cast<uint4*>(outs[q] + row_base + head + v * EPV) =
+                    make_vector<OUT>((int8_t)((cur2 >> (8 * q)) & 0xff), (int8_t)((nxt2 >> (8 * q)) & 0xff), e_cross);
+            }
             v += 32;
             col += step_col;
             rem += step_rem;
@@ -286,29 +351,33 @@ __global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict_
 #pragma unroll
         for (int u = 0; u < kUpVec; ++u) {
           if (v >= nvec) break;
-          OUT* dst = row + head + v * EPV;
-          OUT vals[EPV];
-          const int8_t cur = col < T ? src[col * 128] : (int8_t)0;
-          if (simple) {
-            const int8_t nxt = col + 1 < T ? src[(col + 1) * 128] : (int8_t)0;
-            // samples e with rem + e*fs < sr stay in `col`: e_cross = ceil((sr - rem) / fs)
-            const int e_cross = (int)__umulhi((unsigned)(sr - rem + fs - 1), fs_magic);
-            make_vector<OUT>(vals, cur, nxt, e_cross);
-          } else {
-            int64_t c2 = col;
-            int r2 = rem;
-            int8_t cv = cur;
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            const int8_t* src = planes[q] + src_off;
+            OUT* dst = outs[q] + row_base + head + v * EPV;
+            const int8_t cur = col < T ? src[col * 128] : (int8_t)0;
+            if (simple) {
+              const int8_t nxt = col + 1 < T ? src[(col + 1) * 128] : (int8_t)0;
+              // samples e with rem + e*fs < sr stay in `col`: e_cross = ceil((sr - rem) / fs)
+              const int e_cross = (int)__umulhi((unsigned)(sr - rem + fs - 1), fs_magic);
+              *reinterpret_cast<uint4*>(dst) = make_vector<OUT>(cur, nxt, e_cross);
+            } else {
+              OUT vals[EPV];
+              int64_t c2 = col;
+              int r2 = rem;
+              int8_t cv = cur;
 #pragma unroll 1
-            for (int e = 0; e < EPV; ++e) {
-              vals[e] = (OUT)cv;
-              r2 += fs;
-              if (r2 >= sr) {
-                do { r2 -= sr; ++c2; } while (r2 >= sr);
-                cv = c2 < T ? src[c2 * 128] : (int8_t)0;
+              for (int e = 0; e < EPV; ++e) {
+                vals[e] = (OUT)cv;
+                r2 += fs;
+                if (r2 >= sr) {
+                  do { r2 -= sr; ++c2; } while (r2 >= sr);
+                  cv = c2 < T ? src[c2 * 128] : (int8_t)0;
+                }
               }
+              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals);
             }
           }
-          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals);
           v += 32;
           col += step_col;
           rem += step_rem;
@@ -435,29 +504,59 @@ int mst_pianoroll_chunks(const void* d_plane, int64_t n_rows, int num_chunks, in
   return MST_OK;
 }
 
-int mst_pianoroll_upsample(const void* d_plane, const int64_t* d_row_offsets, const int64_t* d_sample_offsets,
-                           int n_pieces, int64_t total_samples, int fs, int sr, int pitch_lo, int n_keys, int out_dtype,
-                           void* d_out, mst_stream_t stream) {
+static int launch_upsample(const void* d_plane0, const void* d_plane1, const int64_t* d_row_offsets,
+                           const int64_t* d_sample_offsets, int n_pieces, int64_t total_samples, int fs, int sr, int pitch_lo,
+                           int n_keys, int out_dtype, void* d_out0, void* d_out1, mst_stream_t stream) {
   if (n_pieces <= 0 || fs <= 0 || sr <= 0 || pitch_lo < 0 || n_keys <= 0 || pitch_lo + n_keys > 128)
     return fail(MST_ERR_INVALID, "bad upsample geometry");
+  if ((int64_t)32 * 16 * fs + sr >= ((int64_t)1 << 32)) return fail(MST_ERR_INVALID, "fs / sr too large");
   if (total_samples <= 0) return MST_OK;
-  if (!d_row_offsets || !d_sample_offsets || !d_out) return fail(MST_ERR_INVALID, "null argument");
+  if (!d_row_offsets || !d_sample_offsets || !d_out0) return fail(MST_ERR_INVALID, "null argument");
   // d_plane may be NULL only when every piece has an empty roll (all output samples are then zero)
+  const bool two = d_out1 != nullptr;
+  if (two && ((reinterpret_cast<uintptr_t>(d_out0) ^ reinterpret_cast<uintptr_t>(d_out1)) & 15))
+    return fail(MST_ERR_INVALID, "the two output planes must have the same alignment modulo 16 bytes");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int64_t avg = total_samples / n_pieces + 1;
   const int epv = out_dtype == MST_DTYPE_I8 ? 16 : 4;
   const int64_t chunks = (avg / epv + 32 * kUpVec - 1) / (32 * kUpVec);  // warp-chunks per key row (average piece)
-  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (chunks + 7) / 8));
+  // each CTA (8 warps) walks >= 4 rounds of chunks of its row when the grid is large enough to fill the GPU anyway
+  const int64_t rows = (int64_t)n_keys * n_pieces;
+  int64_t per_cta = rows >= 8 * 148 ? 32 : 8;
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (chunks + per_cta - 1) / per_cta));
   dim3 grid(gx, (unsigned)n_keys, (unsigned)std::min(n_pieces, 65535));
-  const int8_t* src = reinterpret_cast<const int8_t*>(d_plane);
+  const int8_t* p0 = reinterpret_cast<const int8_t*>(d_plane0);
+  const int8_t* p1 = reinterpret_cast<const int8_t*>(d_plane1);
   switch (out_dtype) {
-    case MST_DTYPE_I8: upsample_kernel<int8_t><<<grid, 256, 0, s>>>(src, d_row_offsets, d_sample_offsets, n_pieces, fs, sr, pitch_lo, n_keys, (int8_t*)d_out); break;
-    case MST_DTYPE_F32: upsample_kernel<float><<<grid, 256, 0, s>>>(src, d_row_offsets, d_sample_offsets, n_pieces, fs, sr, pitch_lo, n_keys, (float*)d_out); break;
+    case MST_DTYPE_I8:
+      if (two) upsample_kernel<int8_t, 2><<<grid, 256, 0, s>>>(p0, p1, d_row_offsets, d_sample_offsets, n_pieces, fs, sr, pitch_lo, n_keys, (int8_t*)d_out0, (int8_t*)d_out1);
+      else upsample_kernel<int8_t, 1><<<grid, 256, 0, s>>>(p0, p0, d_row_offsets, d_sample_offsets, n_pieces, fs, sr, pitch_lo, n_keys, (int8_t*)d_out0, (int8_t*)d_out0);
+      break;
+    case MST_DTYPE_F32:
+      if (two) upsample_kernel<float, 2><<<grid, 256, 0, s>>>(p0, p1, d_row_offsets, d_sample_offsets, n_pieces, fs, sr, pitch_lo, n_keys, (float*)d_out0, (float*)d_out1);
+      else upsample_kernel<float, 1><<<grid, 256, 0, s>>>(p0, p0, d_row_offsets, d_sample_offsets, n_pieces, fs, sr, pitch_lo, n_keys, (float*)d_out0, (float*)d_out0);
+      break;
     default: return fail(MST_ERR_UNSUPPORTED, "upsample out_dtype must be int8 or float32");
   }
   MST_CUDA_OK(cudaGetLastError());
   count_launch();
   return MST_OK;
+}
+
+int mst_pianoroll_upsample(const void* d_plane, const int64_t* d_row_offsets, const int64_t* d_sample_offsets,
+                           int n_pieces, int64_t total_samples, int fs, int sr, int pitch_lo, int n_keys, int out_dtype,
+                           void* d_out, mst_stream_t stream) {
+  return launch_upsample(d_plane, nullptr, d_row_offsets, d_sample_offsets, n_pieces, total_samples, fs, sr, pitch_lo, n_keys,
+                         out_dtype, d_out, nullptr, stream);
+}
+
+int mst_pianoroll_upsample_pair(const void* d_roll, const void* d_onoff, const int64_t* d_row_offsets,
+                                const int64_t* d_sample_offsets, int n_pieces, int64_t total_samples, int fs, int sr,
+                                int pitch_lo, int n_keys, int out_dtype, void* d_out_roll, void* d_out_onoff,
+                                mst_stream_t stream) {
+  if (total_samples > 0 && !d_out_onoff) return fail(MST_ERR_INVALID, "null argument");
+  return launch_upsample(d_roll, d_onoff, d_row_offsets, d_sample_offsets, n_pieces, total_samples, fs, sr, pitch_lo, n_keys,
+                         out_dtype, d_out_roll, d_out_onoff, stream);
 }
 
 }  // extern "C"

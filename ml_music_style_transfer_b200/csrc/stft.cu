@@ -1,7 +1,7 @@
 // P1 / P2: framing + Hann window + 2048-point real FFT with the epilogue fused in: complex spectrum, magnitude, power,
 // log1p(power), or -- for the mel path -- the power spectrum as split-precision bf16 (hi, lo) rows handed to the
 // tcgen05 projection kernel in mel_gemm.cu through an L2-resident ring.  One warp per frame, persistent CTAs of
-// 8 warps walking tiles of 8 consecutive frames of one clip.
+// kWarpsPerCta warps walking tiles of kWarpsPerCta consecutive frames of one clip.
 //
 // Replaces librosa.stft + np.log1p(np.abs(.)**2) (reference preprocessing/preprocess.py:47-57) and, together with
 // mel_gemm.cu, librosa.feature.melspectrogram (reference tests/plot_spec.py:20).
@@ -16,7 +16,9 @@ namespace mst {
 
 constexpr int kModeConv = 5;          // internal epilogue: per-clip sums of (|S| - S_target)^2 and S_target^2 (spectral convergence)
 constexpr int kModeSplit = 4;         // internal epilogue: |S|^2 as split bf16 (hi, lo) rows for the tensor-core mel projection
-constexpr int kTileStride = 1028;     // floats per frame row of the bin-major staging tile (== 4 mod 32: conflict-free)
+constexpr int kRowsPerWarp = 32 / kWarpsPerCta;       // bin rows one warp stores per trip of the bin-major epilogue (3 at 10 warps)
+constexpr int kTileStride = 1024 + kRowsPerWarp;     // floats per frame row of the bin-major staging tile: bank = (stride * f + k) % 32 is
+                                                       // distinct over the (frame, row) pairs of a warp -> conflict-free reads
 
 struct SplitOut {          // ring of split-precision power-spectrum rows (kSpecPad bf16 each), consumed by mel_gemm.cu
   __nv_bfloat16* hi;
@@ -58,9 +60,7 @@ __device__ __forceinline__ void load_frame(float2 (&v)[32], const float* __restr
   }
 #pragma unroll
   for (int r = 0; r < 32; ++r) {
-    const float2 w = w2[32 * r + lane];
-    v[r].x *= w.x;
-    v[r].y *= w.y;
+    v[r] = pk_mul(v[r], w2[32 * r + lane]);
   }
 }
 
@@ -222,13 +222,15 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
       }
     }
     if (layout == MST_LAYOUT_BIN_MAJOR) {
-      // transposed store: clip block is [n_out][T]; 8 consecutive frames give 32-byte row segments
+      // transposed store: clip block is [n_out][T]; the tile's consecutive frames give one contiguous segment per bin row,
+      // a warp stores kRowsPerWarp rows per trip (lane = (row, frame))
       __syncthreads();
       const int nvalid = min(kWarpsPerCta, cd.frames - t0);
-      const int f = threadIdx.x & 7, kk = threadIdx.x >> 3;
+      const int f = lane % kWarpsPerCta, rr = lane / kWarpsPerCta;
       float* blk = out + cd.frame_offset * n_out;
-      if (f < nvalid) {
-        for (int k = kk; k < n_out; k += 32) blk[(int64_t)k * cd.frames + t0 + f] = s_tile[f * kTileStride + k];
+      if (rr < kRowsPerWarp && f < nvalid) {
+        for (int k = warp * kRowsPerWarp + rr; k < n_out; k += kRowsPerWarp * kWarpsPerCta)
+          blk[(int64_t)k * cd.frames + t0 + f] = s_tile[f * kTileStride + k];
       }
       __syncthreads();
     }
@@ -386,7 +388,7 @@ int mst_stft_mel_f32(const float* d_audio, const mst_batch_t* b, const mst_mel_p
   SplitOut split;
   split.hi = reinterpret_cast<__nv_bfloat16*>(ws);
   split.lo = split.hi + ring_rows * kSpecPad;
-  const int chunk_tiles = (int)(ring_rows / kWarpsPerCta);  // a tile holds at most 8 frames
+  const int chunk_tiles = (int)(ring_rows / kWarpsPerCta);  // a tile holds at most kWarpsPerCta frames
   int c = 0;                                                // clip cursor (tiles are ordered by clip)
   for (int tile0 = 0; tile0 < b->total_tiles; tile0 += chunk_tiles) {
     const int tile1 = std::min(b->total_tiles, tile0 + chunk_tiles);

@@ -211,6 +211,25 @@ at::Tensor pianoroll_upsample(const at::Tensor& plane, const at::Tensor& row_off
   return out;
 }
 
+std::tuple<at::Tensor, at::Tensor> pianoroll_upsample_pair(const at::Tensor& roll, const at::Tensor& onoff,
+                                                           const at::Tensor& row_offsets, const at::Tensor& sample_offsets,
+                                                           int64_t total_samples, int64_t fs, int64_t sr, int64_t pitch_lo,
+                                                           int64_t n_keys, int64_t out_dtype) {
+  for (const at::Tensor* t : {&roll, &onoff})
+    TORCH_CHECK(t->is_cuda() && t->is_contiguous() && t->dim() == 2 && t->size(1) == 128 &&
+                (t->scalar_type() == at::kByte || t->scalar_type() == at::kChar), "planes must be CUDA (T,128) int8/uint8 tensors");
+  TORCH_CHECK(roll.size(0) == onoff.size(0) && roll.get_device() == onoff.get_device(), "roll / onoff do not match");
+  want(row_offsets, at::kLong, "row_offsets"); want(sample_offsets, at::kLong, "sample_offsets");
+  c10::cuda::CUDAGuard guard(roll.device());
+  at::Tensor a = at::empty({n_keys * total_samples}, roll.options().dtype(dtype_of(out_dtype)));
+  at::Tensor b = at::empty({n_keys * total_samples}, roll.options().dtype(dtype_of(out_dtype)));
+  check(mst_pianoroll_upsample_pair(roll.data_ptr(), onoff.data_ptr(), row_offsets.data_ptr<int64_t>(),
+                                    sample_offsets.data_ptr<int64_t>(), (int)(row_offsets.numel() - 1), total_samples, (int)fs,
+                                    (int)sr, (int)pitch_lo, (int)n_keys, (int)out_dtype, a.data_ptr(), b.data_ptr(), cur_stream()),
+        "mst_pianoroll_upsample_pair");
+  return {a, b};
+}
+
 at::Tensor griffinlim(const at::Tensor& S, int64_t s_layout, bool s_is_log1p_power, int64_t batch, int64_t n_iter,
                       double momentum, const c10::optional<at::Tensor>& init_phase, int64_t init_mode, int64_t seed) {
   want(S, at::kFloat, "S");
@@ -288,6 +307,8 @@ TORCH_LIBRARY(mst_b200, m) {
   m.def("pianoroll_chunks(Tensor plane, int num_chunks, int chunk_rows, int stride_rows, int out_dtype) -> Tensor");
   m.def("pianoroll_upsample(Tensor plane, Tensor row_offsets, Tensor sample_offsets, int total_samples, int fs, int sr, "
         "int pitch_lo, int n_keys, int out_dtype) -> Tensor");
+  m.def("pianoroll_upsample_pair(Tensor roll, Tensor onoff, Tensor row_offsets, Tensor sample_offsets, int total_samples, "
+        "int fs, int sr, int pitch_lo, int n_keys, int out_dtype) -> (Tensor, Tensor)");
   m.def("resample(Tensor x, int sr_in, int sr_out) -> Tensor");
   m.def("spectral_convergence(Tensor y, int batch, Tensor S, int s_layout) -> Tensor");
   m.def("griffinlim(Tensor S, int s_layout, bool s_is_log1p_power, int batch, int n_iter, float momentum, "
@@ -302,6 +323,7 @@ TORCH_LIBRARY_IMPL(mst_b200, CUDA, m) {
   m.impl("pianoroll_merge_instruments", &pianoroll_merge_instruments);
   m.impl("pianoroll_chunks", &pianoroll_chunks);
   m.impl("pianoroll_upsample", &pianoroll_upsample);
+  m.impl("pianoroll_upsample_pair", &pianoroll_upsample_pair);
   m.impl("griffinlim", &griffinlim);
   m.impl("resample", &resample);
   m.impl("spectral_convergence", &spectral_convergence);

@@ -193,20 +193,33 @@ def chunks(plane, num_chunks, chunk_rows, stride_rows, dtype=torch.float64):
     return _lib.ops().pianoroll_chunks(plane, int(num_chunks), int(chunk_rows), int(stride_rows), DTYPE_CODES[dtype])
 
 
+def _sample_offsets(n_pieces, samples_per_piece, device):
+    if np.ndim(samples_per_piece) == 0:  # uniform pieces: offsets built on the device, nothing crosses PCIe
+        so = np.arange(n_pieces + 1, dtype=np.int64) * int(samples_per_piece)
+        return so, torch.arange(n_pieces + 1, dtype=torch.int64, device=device) * int(samples_per_piece)
+    spp = np.asarray(samples_per_piece, dtype=np.int64)
+    so = np.zeros(n_pieces + 1, dtype=np.int64)
+    np.cumsum(spp, out=so[1:])
+    return so, torch.from_numpy(so).pin_memory().to(device, non_blocking=True)
+
+
+def upsample_pair(roll, onoff, row_offsets, samples_per_piece, fs, sr, pitch_lo=21, n_keys=88, dtype=torch.int8):
+    """Roll AND on/off to the audio rate in ONE launch (shared index arithmetic): -> (up_roll, up_onoff, sample_offsets),
+    each laid out like ``upsample``'s result."""
+    n_pieces = int(row_offsets.numel()) - 1
+    so, sample_offsets = _sample_offsets(n_pieces, samples_per_piece, roll.device)
+    a, b = _lib.ops().pianoroll_upsample_pair(roll, onoff, row_offsets, sample_offsets, int(so[-1]), int(fs), int(sr),
+                                              int(pitch_lo), int(n_keys), DTYPE_CODES[dtype])
+    return a, b, so
+
+
 def upsample(plane, row_offsets, samples_per_piece, fs, sr, pitch_lo=21, n_keys=88, dtype=torch.int8):
     """Hold-replicate a frame-rate plane to the audio rate: per piece (n_keys, N_p), col(n) = (n*fs)//sr.
 
     Returns (flat tensor, sample_offsets); piece p's block is flat[n_keys*off[p] : n_keys*off[p+1]].view(n_keys, N_p).
     """
     n_pieces = int(row_offsets.numel()) - 1
-    if np.ndim(samples_per_piece) == 0:  # uniform pieces: offsets built on the device, nothing crosses PCIe
-        so = np.arange(n_pieces + 1, dtype=np.int64) * int(samples_per_piece)
-        sample_offsets = torch.arange(n_pieces + 1, dtype=torch.int64, device=plane.device) * int(samples_per_piece)
-    else:
-        spp = np.asarray(samples_per_piece, dtype=np.int64)
-        so = np.zeros(n_pieces + 1, dtype=np.int64)
-        np.cumsum(spp, out=so[1:])
-        sample_offsets = torch.from_numpy(so).pin_memory().to(plane.device, non_blocking=True)
+    so, sample_offsets = _sample_offsets(n_pieces, samples_per_piece, plane.device)
     out = _lib.ops().pianoroll_upsample(plane, row_offsets, sample_offsets, int(so[-1]), int(fs), int(sr), int(pitch_lo),
                                         int(n_keys), DTYPE_CODES[dtype])
     return out, so

@@ -113,8 +113,8 @@ class HostPipeline:
                 for s in range(0, m, self.plane_sub):
                     e = min(m, s + self.plane_sub)
                     ro = row_off[s:e + 1]
-                    ua, ub = PR.upsample_pair(roll, onoff, ro, self.clip_len, self.roll_fs, self.sr, self.pitch_lo,
-                                              self.n_keys, torch.int8)
+                    ua, ub, _ = PR.upsample_pair(roll, onoff, ro, self.clip_len, self.roll_fs, self.sr, self.pitch_lo,
+                                                 self.n_keys, torch.int8)
                     if self.planes_to_host:
                         k = (e - s) * self.n_keys * self.clip_len
                         self.h_planes[si][:k].copy_(ua, non_blocking=True)

@@ -71,7 +71,7 @@ def test_griffinlim_multi_launch_path_32_iterations(pkg, gpu):
     ph = torch.from_numpy(np.stack(u_list)).to(gpu)
     gb = F.ClipBatch.from_frames([T] * n_clips, hop, device=gpu)
     props = torch.cuda.get_device_properties(gpu)
-    assert n_clips * ((T + 7) // 8) > 2 * props.multi_processor_count
+    assert n_clips * ((T + 7) // 8) > 2 * props.multi_processor_count     # tiles of 8 frames
     n0 = pkg._lib.launch_count()
     out = F.griffinlim_batch(S, gb, n_iter=n_iter, init_phase=ph, layout=F.BIN_MAJOR)
     launched = pkg._lib.launch_count() - n0
@@ -195,11 +195,25 @@ def test_c3_1000_pieces_30s_bit_exact(pkg, gpu):
         ref_r, ref_o = refs[i]
         assert np.array_equal(up.view(88, N30).cpu().numpy(), opr.upsample_to_audio_rate(ref_r, fs, SR, N30, 21, 88, np.int8)), i
         assert np.array_equal(up_o.view(88, N30).cpu().numpy(), opr.upsample_to_audio_rate(ref_o, fs, SR, N30, 21, 88, np.int8)), i
+    # dense worst case for the non-uniform path: a roll that toggles every column (no chunk is uniform)
+    T = int(ro[1] - ro[0])
+    dense = torch.zeros((T, 128), dtype=torch.uint8, device=gpu)
+    dense[::2, 21:109:2] = 1
+    dense[1::2, 22:109:2] = 1
+    d_on = torch.zeros((T, 128), dtype=torch.int8, device=gpu)
+    d_on[0] = dense[0].to(torch.int8)
+    d_on[1:] = dense[1:].to(torch.int8) - dense[:-1].to(torch.int8)
+    ro1 = torch.tensor([0, T], dtype=torch.int64, device=gpu)
+    da, db, _ = P.upsample_pair(dense, d_on, ro1, N30, fs, SR, 21, 88, torch.int8)
+    assert np.array_equal(da.view(88, N30).cpu().numpy(), opr.upsample_to_audio_rate(dense.cpu().numpy(), fs, SR, N30, 21, 88, np.int8))
+    assert np.array_equal(db.view(88, N30).cpu().numpy(), opr.upsample_to_audio_rate(d_on.cpu().numpy(), fs, SR, N30, 21, 88, np.int8))
     # all eight in ONE launch (the batched form the benchmark uses) == the per-piece launches
     ro8 = torch.zeros(9, dtype=torch.int64)
     rows8 = [roll[ro[i]:ro[i + 1]] for i in sel]
     np.cumsum([r.shape[0] for r in rows8], out=ro8.numpy()[1:])
-    up8, so8 = P.upsample(torch.cat(rows8), ro8.to(gpu), N30, fs, SR, 21, 88, torch.int8)
-    up8 = up8.view(8, 88, N30)
+    oo8 = [onoff[ro[i]:ro[i + 1]] for i in sel]
+    up8, upo8, so8 = P.upsample_pair(torch.cat(rows8), torch.cat(oo8), ro8.to(gpu), N30, fs, SR, 21, 88, torch.int8)
+    up8, upo8 = up8.view(8, 88, N30), upo8.view(8, 88, N30)
     for j, i in enumerate(sel):
         assert np.array_equal(up8[j].cpu().numpy(), opr.upsample_to_audio_rate(refs[i][0], fs, SR, N30, 21, 88, np.int8)), i
+        assert np.array_equal(upo8[j].cpu().numpy(), opr.upsample_to_audio_rate(refs[i][1], fs, SR, N30, 21, 88, np.int8)), i

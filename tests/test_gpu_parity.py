@@ -269,6 +269,12 @@ def test_pianoroll_batch_bit_exact(pkg, gpu, fs, sr, pitch_lo, n_keys):
     n_samp = [int(sr * 1.5) + 7 * i for i in range(len(pieces))]
     up, so = P.upsample(roll, row_off, n_samp, fs, sr, pitch_lo, n_keys, torch.int8)
     up_oo, _ = P.upsample(onoff, row_off, n_samp, fs, sr, pitch_lo, n_keys, torch.float32)
+    # roll + on/off in ONE launch (shared index arithmetic) == the two single-plane launches, int8 and float32
+    pa, pb, so2 = P.upsample_pair(roll, onoff, row_off, n_samp, fs, sr, pitch_lo, n_keys, torch.int8)
+    up_oo8, _ = P.upsample(onoff, row_off, n_samp, fs, sr, pitch_lo, n_keys, torch.int8)
+    assert np.array_equal(so2, so) and torch.equal(pa, up) and torch.equal(pb, up_oo8)
+    fa, fb, _ = P.upsample_pair(roll, onoff, row_off, n_samp, fs, sr, pitch_lo, n_keys, torch.float32)
+    assert torch.equal(fb, up_oo) and torch.equal(fa, up.to(torch.float32))
     up, up_oo = up.cpu().numpy(), up_oo.cpu().numpy()
     for i, (p, v, s, e) in enumerate(pieces):
         ref_v = opr.get_piano_roll(p, v, s, e, fs)
@@ -743,16 +749,23 @@ def test_host_pipeline_matches_direct_calls(pkg, gpu):
     plan = F.MelPlan.get(22050, device=gpu)
     mel = F.melspectrogram_batch(audio, batch, plan, log1p=True, layout=F.BIN_MAJOR).cpu()
     assert torch.equal(pipe.h_mel, mel)
-    nb = PR.NoteBatch(*notes, device=gpu)
+    # the pipeline rasterises every piece over the clip's duration: piece i owns rows [i * rows_per_clip, (i + 1) * rows_per_clip)
+    nb = PR.NoteBatch(*notes, device=gpu, end_times=[clip_len / 22050.0] * n)
     roll, onoff, row_off, _ = PR.rasterize(nb, 250)
-    ro = row_off.cpu().numpy()
-    for i in (0, 299, 300, 599):  # both sides of the chunk boundary
-        r = min(int(ro[i + 1] - ro[i]), pipe.rows_per_clip)
-        # the pipeline packs each chunk's rows back to back starting at chunk_start * rows_per_clip
-        c0 = 0 if i < 300 else 300
-        base = c0 * pipe.rows_per_clip + int(ro[i] - ro[c0])
-        assert torch.equal(pipe.h_roll[base:base + r], roll[ro[i]:ro[i] + r].cpu())
-        assert torch.equal(pipe.h_onoff[base:base + r], onoff[ro[i]:ro[i] + r].cpu())
+    assert pipe.rows_per_clip == 250 and roll.shape[0] == n * pipe.rows_per_clip
+    assert torch.equal(pipe.h_roll, roll.cpu()) and torch.equal(pipe.h_onoff, onoff.cpu())
+    for i in (0, 299, 300, 599):  # both sides of the chunk boundary, against the oracle
+        p_, v_, s_, e_ = pieces[i]
+        ref_r, ref_o = opr.binarize_and_onoff(opr.get_piano_roll(p_, v_, s_, e_, 250, end_time=1.0))
+        blk = slice(i * 250, (i + 1) * 250)
+        assert np.array_equal(pipe.h_roll[blk].numpy(), ref_r) and np.array_equal(pipe.h_onoff[blk].numpy(), ref_o)
+    # a second run with different notes re-stages them (nothing is cached between runs)
+    notes2 = tuple(np.concatenate([p[j] for p in pieces[::-1]]) for j in range(4)) + \
+        (np.concatenate([[0], np.cumsum([len(p[0]) for p in pieces[::-1]])]).astype(np.int64),)
+    pipe.run(h_audio, h_S, notes2)
+    p_, v_, s_, e_ = pieces[n - 1]
+    assert np.array_equal(pipe.h_roll[:250].numpy(), opr.binarize_and_onoff(opr.get_piano_roll(p_, v_, s_, e_, 250, end_time=1.0))[0])
+    pipe.run(h_audio, h_S, notes)
     # Griffin-Lim: the random phase stream differs per chunk, so compare convergence, clip by clip
     L = 512 * (T - 1)
     for i in (0, 450):

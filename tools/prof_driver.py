@@ -29,6 +29,6 @@ for rep in range(3):
         F.griffinlim_batch(S, gl_batch, n_iter=4, seed=1, layout=F.FRAME_MAJOR)
     if "roll" in stages:
         roll, onoff, ro, _ = PR.rasterize(notes, bench.ROLL_FS)
-        PR.upsample(roll, ro, bench.CLIP_LEN, bench.ROLL_FS, bench.SR, 21, 88, torch.int8)
+        PR.upsample_pair(roll, onoff, ro, bench.CLIP_LEN, bench.ROLL_FS, bench.SR, 21, 88, torch.int8)
     torch.cuda.synchronize()
 print("ok")
