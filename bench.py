@@ -219,10 +219,22 @@ def run_ours(args):
     launches = pkg._lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    # reference point for the write-only stage: what a plain device fill achieves on this GPU (measured live)
+    # reference point for the write-only stage: what the driver's own device memset achieves on this GPU (measured live;
+    # tools/ubench.cu has the full study: memset 7.4 TB/s, one-shot st.global.v4 grid 7.6, grid-stride 6.2-6.9, bulk
+    # (TMA) stores 6.4 -- torch's fill_ kernel, which round 1 took for the write ceiling, only reaches 3.9)
     fill_buf = torch.empty(2 * 1024 ** 3, dtype=torch.int8, device=device)
-    fill_buf.fill_(1)
-    fill_ms = float(np.median(timed(lambda: fill_buf.fill_(1), 5)))
+    try:
+        from cuda.bindings import runtime as cudart   # cuda-python: the driver's memset, not a torch kernel
+    except Exception:  # noqa: BLE001
+        cudart = None
+
+    def _memset():
+        if cudart is not None:
+            cudart.cudaMemsetAsync(fill_buf.data_ptr(), 1, fill_buf.numel(), torch.cuda.current_stream().cuda_stream)
+        else:
+            fill_buf.fill_(1)
+    _memset()
+    fill_ms = float(np.median(timed(_memset, 5)))
     write_peak = fill_buf.numel() / (fill_ms * 1e-3) / 1e9
     del fill_buf
 
@@ -254,7 +266,7 @@ def run_ours(args):
     # ---- optional final gather of the features over NCCL (north_star: "NCCL over NVLink used only for the optional
     # final gather"); measured separately, never part of `value` -------------------------------------------------------
     gather = None
-    if args.gather and world > 1:
+    if world > 1 and not args.no_gather:
         from ml_music_style_transfer_b200 import sharding
         feats = stage_a().view(n_clips, N_MELS * T_FRAMES)
         sharding.gather_features(feats, n_clips * world)
@@ -270,6 +282,42 @@ def run_ours(args):
         gather = {"ms": float(gms.item()), "bytes_received_per_rank": int(full.numel() * 4), "own_shard_intact": ok,
                   "algbw_gbs": full.numel() * 4 / (float(gms.item()) * 1e-3) / 1e9}
         del full, feats
+
+    # ---- strong scaling (N > 1): the SAME 16384-clip C4 batch split over the ranks (the weak line above gives every rank
+    # its own 16384 clips); no data-path collective either way, so this measures launch / tail overheads at small shards ----
+    strong = None
+    if world > 1 and not args.no_strong and args.workload == "c4":
+        from ml_music_style_transfer_b200 import sharding
+        s0, s1 = sharding.shard_range(n_clips, rank, world)
+        m = s1 - s0
+        batch_s = F.ClipBatch.uniform(m, CLIP_LEN, HOP, device=device)
+        gl_s = F.ClipBatch.from_frames([T_FRAMES] * m, HOP, device=device)
+        offs = notes_h[4]
+        notes_s = PR.NoteBatch(*[a[:offs[m]] for a in notes_h[:4]], offs[:m + 1], device=device)
+
+        def step_s():
+            F.melspectrogram_batch(audio[:m * CLIP_LEN], batch_s, plan, log1p=True, layout=F.BIN_MAJOR)
+            roll, onoff, row_off, _ = PR.rasterize(notes_s, ROLL_FS)
+            for q0 in range(0, m, roll_sub):
+                q1 = min(m, q0 + roll_sub)
+                PR.upsample_pair(roll, onoff, row_off[q0:q1 + 1], CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
+            return F.griffinlim_batch(S[:m * T_FRAMES * K], gl_s, n_iter=GL_ITERS, momentum=0.99, init="random", seed=7,
+                                      layout=F.FRAME_MAJOR)
+        for _ in range(3):
+            step_s()
+        barrier()
+        k_s = max(3, min(args.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k_s):
+            step_s()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / k_s], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "total_clips": n_clips, "clips_per_gpu": m, "steps": k_s, "ms_per_step": float(t.item()),
+                  "value": n_clips * CLIP_SECONDS / (float(t.item()) * 1e-3), "unit": "audio-s/s"}
+        del batch_s, gl_s, notes_s
 
     # ---- configs[0]/[1] of BASELINE.json: ONE 30 s clip (latency view; tiny against a B200, reported for completeness) ----
     single = None
@@ -311,8 +359,9 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, pkg, F, PR, device, audio, S, notes_h, plan, world, barrier)
-        try:   # the 15 MB-per-clip variant is informative only: never let it take the main line down
-            e2e_all = run_e2e(args, pkg, F, PR, device, audio, S, notes_h, plan, world, barrier, planes_to_host=True)
+        try:   # the 15 MB-per-clip variant is informative only (and 62 GB of D2H per 4096 clips): fewer clips, never fatal
+            e2e_all = run_e2e(args, pkg, F, PR, device, audio, S, notes_h, plan, world, barrier, planes_to_host=True,
+                              n=min(args.e2e_clips, 2048))
         except Exception as exc:  # noqa: BLE001
             e2e_all = {"error": repr(exc)}
 
@@ -333,11 +382,14 @@ def run_ours(args):
                              "fp32_frac": n_clips * T_FRAMES * 133140.0 * GL_ITERS / (mc * 1e-3) / fp32_peak},
         }
         achieved = gl_iter_bytes / (iter_ms * 1e-3) / 1e9
-        traffic = args.traffic
+        traffic, traffic_src = args.traffic, "--traffic"
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if traffic is None and os.path.exists(tpath):
-            with open(tpath) as f:  # ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of one GL iteration
-                traffic = json.load(f)["gl_iteration_dram_bytes_per_clip"] * n_clips
+            with open(tpath) as f:  # ncu: dram__bytes_read.sum + dram__bytes_write.sum of one GL iteration launch
+                tj = json.load(f)
+            traffic = tj["gl_iteration_dram_bytes_per_clip"] * n_clips
+            traffic_src = tj.get("source", "profiles/traffic.json") + ("" if tj.get("clips") == n_clips else
+                                                                          f" -- scaled from {tj.get('clips')} to {n_clips} clips")
         line = {
             "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -353,7 +405,11 @@ def run_ours(args):
             "stages": stages,
             "roofline": {"bound": "hbm", "kernel": "gl_kernel<false> (one Griffin-Lim iteration)", "achieved": achieved,
                          "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "ms_per_launch": iter_ms, "algorithmic_bytes_per_launch": gl_iter_bytes, "traffic": traffic},
+                         "ms_per_launch": iter_ms, "algorithmic_bytes_per_launch": gl_iter_bytes, "traffic": traffic,
+                         # the kernel never stores the phase, so its real DRAM traffic is below the algorithmic figure:
+                         # dram_frac = measured DRAM bytes / time / peak is the honest utilisation of the HBM pipe
+                         "dram_frac": (traffic / (iter_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                         "traffic_source": traffic_src},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall_s,
         }
         if not args.no_single:
@@ -361,6 +417,8 @@ def run_ours(args):
             line["extras"] = extras
         if gather is not None:
             line["final_gather_logmel"] = gather
+        if strong is not None:
+            line["strong_scaling"] = strong
         if e2e is not None:
             line["e2e"] = e2e
             line["e2e_planes_to_host"] = e2e_all
@@ -372,33 +430,120 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrier, planes_to_host=False):
-    """Same step through host buffers via the package's public ``pipeline.HostPipeline``: pinned host -> device copies
-    and device -> host reads are inside the timing.
+def host_memory_available():
+    """Bytes of host memory this process may still use: MemAvailable, bounded by the cgroup limit when there is one."""
+    avail = 64 << 30
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    avail = int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    for path, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                      ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            with open(path) as f:
+                lim = f.read().strip()
+            if lim != "max" and int(lim) < (1 << 60):
+                with open(cur) as f:
+                    used = int(f.read().strip())
+                avail = min(avail, int(lim) - used)
+        except (OSError, ValueError):
+            pass
+    return max(avail, 1 << 30)
 
-    Host inputs: audio, magnitude spectrograms (the model output Griffin-Lim inverts), MIDI note arrays.
-    Host outputs: log-mel, reconstructed waveforms, frame-rate piano roll + on/off (what the reference's load_midi
-    returns).  The audio-rate int8 planes are the model's conditioning input and stay on the device by default
-    (15.5 MB per 4 s clip, 45x the audio itself); `planes_to_host=True` also copies them out (reported separately).
-    Chunks rotate over 4 CUDA streams; measured on B200 at 4096 clips: 1 stream 314 ms, 2: 233 ms, 3: 204 ms,
-    4: 197 ms (kernels alone: 181 ms).
+
+def host_copy_ceiling(device, world, barrier, gib=1.0, reps=3):
+    """What the host side of this box gives ONE rank while ALL ranks copy at once: a pinned H2D stream and a pinned D2H
+    stream run concurrently (as they do in the pipeline), barrier-aligned across ranks.  At N = 8 the eight GPUs share
+    the host's memory system / PCIe root, so this -- not the kernels, not NVLink -- bounds `e2e`."""
+    import torch
+    n = int(gib * (1 << 30))
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n, dtype=torch.uint8, device=device)
+    d_out = torch.ones(n, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+    def go():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    go()
+    barrier()
+    a1, b1, a2, b2 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    with torch.cuda.stream(s1):
+        a1.record()
+    with torch.cuda.stream(s2):
+        a2.record()
+    for _ in range(reps):
+        go()
+    with torch.cuda.stream(s1):
+        b1.record()
+    with torch.cuda.stream(s2):
+        b2.record()
+    barrier()
+    h2d, d2h = reps * n / (a1.elapsed_time(b1) * 1e-3) / 1e9, reps * n / (a2.elapsed_time(b2) * 1e-3) / 1e9
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([h2d, d2h], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)   # the slowest rank's share
+        h2d, d2h = [float(x) for x in t.tolist()]
+    return h2d, d2h
+
+
+def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrier, planes_to_host=False, n=None):
+    """Same step through host buffers via the package's public ``pipeline.HostPipeline``: pinned host -> device copies
+    and device -> host reads are inside the timing, and so is the staging of the MIDI note arrays into pinned memory.
+
+    Host inputs: audio, magnitude spectrograms (the model output Griffin-Lim inverts), MIDI note arrays -- FRESH per
+    repetition: every timed run slides a window over a host buffer that holds `reps` extra clips, so no two runs copy the
+    same bytes to the same place.  Host outputs: log-mel, reconstructed waveforms, frame-rate piano roll + on/off (what the
+    reference's load_midi returns).  The audio-rate int8 planes are the model's conditioning input and stay on the device
+    by default (15.5 MB per 4 s clip, 45x the audio itself); `planes_to_host=True` also streams them out (reported
+    separately, on fewer clips).  Chunks rotate over 4 CUDA streams.
     """
     import torch
     from ml_music_style_transfer_b200.pipeline import HostPipeline
-    n = min(args.clips, args.e2e_clips)
-    h_audio = torch.empty(n * CLIP_LEN, dtype=torch.float32).pin_memory()
-    h_audio.copy_(audio_d[:n * CLIP_LEN])
-    h_S = torch.empty(n * T_FRAMES * K, dtype=torch.float32).pin_memory()
-    h_S.copy_(S_d[:n * T_FRAMES * K])
+    n = min(args.clips, args.e2e_clips) if n is None else min(args.clips, n)
+    # page-locked host memory this pass needs per clip (inputs + outputs); never pin more than half of what the host has
+    # free, shared by the ranks of this node (a box driven out of memory would take the whole run down)
+    per_clip = 4 * CLIP_LEN + 4 * T_FRAMES * K + 4 * N_MELS * T_FRAMES + 4 * HOP * (T_FRAMES - 1) + 2 * 128 * int(ROLL_FS * CLIP_SECONDS)
+    n_cap = int(0.5 * host_memory_available() / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))) / per_clip)
+    capped = n_cap < n
+    if capped:
+        n = max(256, (n_cap // 256) * 256)
+    reps = max(1, min(args.steps, 3))
+    extra = min(reps, n)
+    h_audio = torch.empty((n + extra) * CLIP_LEN, dtype=torch.float32).pin_memory()
+    h_audio[:n * CLIP_LEN].copy_(audio_d[:n * CLIP_LEN])
+    h_audio[n * CLIP_LEN:].copy_(audio_d[:extra * CLIP_LEN])
+    fs = T_FRAMES * K
+    h_S = torch.empty((n + extra) * fs, dtype=torch.float32).pin_memory()
+    h_S[:n * fs].copy_(S_d[:n * fs])
+    h_S[n * fs:].copy_(S_d[:extra * fs])
+    offs = np.asarray(notes_h[4], dtype=np.int64)
+
+    def notes_window(k):   # pieces k .. k+n-1 (wrapping), re-based offsets
+        if k == 0:
+            return tuple(a[:offs[n]] for a in notes_h[:4]) + (offs[:n + 1],)
+        lo, hi = int(offs[k]), int(offs[n])
+        parts = [np.concatenate([a[lo:hi], a[:offs[k]]]) for a in notes_h[:4]]
+        sizes = np.concatenate([np.diff(offs[k:n + 1]), np.diff(offs[:k + 1])])
+        return tuple(parts) + (np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64),)
+    windows = [notes_window(k % n) for k in range(reps + 1)]   # built outside the timing: they are the caller's inputs
+
     pipe = HostPipeline(n, CLIP_LEN, sr=SR, hop=HOP, n_mels=N_MELS, roll_fs=ROLL_FS, pitch_lo=PITCH_LO, n_keys=N_KEYS,
                         gl_iters=GL_ITERS, n_chunks=args.e2e_chunks, planes_to_host=planes_to_host, device=device, plan=plan)
-    pipe.run(h_audio, h_S, notes_h)
+    pipe.run(h_audio[:n * CLIP_LEN], h_S[:n * fs], windows[0])
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(1, min(args.steps, 3))
     ev0.record()
-    for _ in range(reps):
-        pipe.run(h_audio, h_S, notes_h)
+    for r in range(reps):
+        k = (r + 1) % (extra + 1)
+        pipe.run(h_audio[k * CLIP_LEN:(k + n) * CLIP_LEN], h_S[k * fs:(k + n) * fs], windows[r + 1])
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1) / reps
@@ -408,11 +553,23 @@ def run_e2e(args, pkg, F, PR, device, audio_d, S_d, notes_h, plan, world, barrie
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     h2d, d2h = pipe.bytes_per_run()
-    return {"value": world * n * CLIP_SECONDS / (ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "clips_per_gpu": n, "ms_per_step": ms, "pipeline_chunks": len(pipe.chunks),
-            "pipeline_streams": pipe.n_streams, "api": "ml_music_style_transfer_b200.pipeline.HostPipeline.run",
-            "outputs_to_host": "log-mel, waveforms, frame-rate roll+onoff" + (", audio-rate planes" if planes_to_host else
-                               " (audio-rate planes stay on the device for the model)")}
+    out = {"value": world * n * CLIP_SECONDS / (ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "clips_per_gpu": n, "ms_per_step": ms, "pipeline_chunks": len(pipe.chunks),
+           "pipeline_streams": pipe.n_streams, "api": "ml_music_style_transfer_b200.pipeline.HostPipeline.run",
+           "capped_by_host_memory": capped,
+           "inputs": "fresh per repetition (sliding window over the host buffers; note arrays re-staged every run)",
+           "outputs_to_host": "log-mel, waveforms, frame-rate roll+onoff" + (", audio-rate planes" if planes_to_host else
+                              " (audio-rate planes stay on the device for the model)")}
+    del pipe, h_audio, h_S
+    if not planes_to_host:
+        bw_h2d, bw_d2h = host_copy_ceiling(device, world, barrier)
+        floor_ms = 1e3 * max(h2d / (bw_h2d * 1e9), d2h / (bw_d2h * 1e9))
+        out["host_copy"] = {"h2d_gbs_per_rank": bw_h2d, "d2h_gbs_per_rank": bw_d2h, "ranks_copying": world,
+                            "copy_floor_ms_per_step": floor_ms,
+                            "note": "pinned H2D + D2H streams running concurrently on every rank at once (slowest rank); "
+                                    "copy_floor = max(h2d_bytes / h2d_bw, d2h_bytes / d2h_bw) is the e2e time the host side "
+                                    "alone allows"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -492,9 +649,11 @@ def main():
                          "in total, sharded over the ranks (strong scaling)")
     ap.add_argument("--clips", type=int, default=None, help="clips per GPU (default: 16384 for c4, 4080/world for c5)")
     ap.add_argument("--gl-sub", type=int, default=16384, help="clips per Griffin-Lim call (workspace bound)")
-    ap.add_argument("--gather", action="store_true", help="also time the optional NCCL all-gather of the log-mel features")
+    ap.add_argument("--gather", action="store_true", help="(default when N > 1) time the optional NCCL all-gather of the log-mel features")
+    ap.add_argument("--no-gather", action="store_true", help="skip the optional final NCCL gather at N > 1")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling pass (16384 clips in total) at N > 1")
     ap.add_argument("--no-single", action="store_true", help="skip the single 30 s clip latency section")
-    ap.add_argument("--e2e-clips", type=int, default=4096, help="clips per GPU for the host-buffer end-to-end pass")
+    ap.add_argument("--e2e-clips", type=int, default=None, help="clips per GPU for the host-buffer end-to-end pass (default: the same as --clips)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline depth of the end-to-end pass (chunks rotating over MST_E2E_STREAMS streams, default 4)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
@@ -511,9 +670,11 @@ def main():
             base, extra = divmod(4080, world)
             args.clips = base + (1 if rank < extra else 0)
         args.gl_sub = min(args.gl_sub, 1024)
-        args.e2e_clips = min(args.e2e_clips, 256)
+        args.e2e_clips = min(args.e2e_clips or 256, 256)
     elif args.clips is None:
         args.clips = 16384
+    if args.e2e_clips is None:
+        args.e2e_clips = args.clips
     if args.impl == "reference":
         run_reference(args)
     else:
