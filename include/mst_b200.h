@@ -173,6 +173,22 @@ int mst_pianoroll_upsample_pair(const void* d_roll, const void* d_onoff, const i
                                 mst_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Mel inversion: librosa.feature.inverse.mel_to_stft, the first half of the
+ * librosa.feature.inverse.mel_to_audio(M, n_iter=300, sr=hp.sr, n_fft=hp.n_fft, hop_length=hp.ws) call kept as a
+ * comment at tests/test_griffinlim.py:24:  S = nnls(mel_basis, M) ** (1 / power), then Griffin-Lim (P4) on S.
+ * Every frame is an independent non-negative least-squares problem min ||A x - m||, x >= 0 (A = the filterbank): start
+ * point max(pinv(A) m, 0) as in librosa.util.nnls, then accelerated projected gradient to `tol` (relative residual) or
+ * `max_iter`.  The plan factorises A A^T once on the host (double precision).
+ * d_mel: FRAME_MAJOR [total_frames][n_mels] or BIN_MAJOR per clip [n_mels][T_c]; `batch` from
+ * mst_batch_create_from_frames; d_S_out: [total_frames][1025] frame-major magnitudes (what mst_griffinlim_f32 consumes in
+ * place). */
+typedef struct mst_mel_inverse_plan mst_mel_inverse_plan_t;
+int mst_mel_inverse_plan_create(const float* h_weights, int n_mels, int n_bins, mst_mel_inverse_plan_t** out);
+void mst_mel_inverse_plan_destroy(mst_mel_inverse_plan_t* p);
+int mst_mel_to_stft_f32(const float* d_mel, int mel_layout, const mst_batch_t* batch, const mst_mel_inverse_plan_t* plan,
+                        float power, int max_iter, float tol, float* d_S_out, mst_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * P4: Griffin-Lim phase reconstruction (fast Griffin-Lim, momentum; momentum=0 is the classic
  * loop kept as a comment at model/inference.py:131-154).
  * Replaces AudioSynthesizer.griffinlim [model/inference.py:105-110]:

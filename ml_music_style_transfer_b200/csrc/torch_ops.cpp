@@ -73,6 +73,15 @@ int64_t mel_plan_create(const at::Tensor& W, int64_t device) {
   return reinterpret_cast<int64_t>(p);
 }
 void mel_plan_destroy(int64_t h) { if (h) mst_mel_plan_destroy(reinterpret_cast<mst_mel_plan_t*>(h)); }
+int64_t mel_inverse_plan_create(const at::Tensor& W, int64_t device) {
+  TORCH_CHECK(W.device().is_cpu() && W.scalar_type() == at::kFloat && W.is_contiguous() && W.dim() == 2,
+              "mel weights must be a contiguous 2-D float32 CPU tensor");
+  c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+  mst_mel_inverse_plan_t* p = nullptr;
+  check(mst_mel_inverse_plan_create(W.data_ptr<float>(), (int)W.size(0), (int)W.size(1), &p), "mst_mel_inverse_plan_create");
+  return reinterpret_cast<int64_t>(p);
+}
+void mel_inverse_plan_destroy(int64_t h) { if (h) mst_mel_inverse_plan_destroy(reinterpret_cast<mst_mel_inverse_plan_t*>(h)); }
 int64_t launch_count() { return mst_launch_count(); }
 
 // ---- device ops --------------------------------------------------------------------------------
@@ -254,6 +263,21 @@ at::Tensor griffinlim(const at::Tensor& S, int64_t s_layout, bool s_is_log1p_pow
   return y;
 }
 
+at::Tensor mel_to_stft(const at::Tensor& mel, int64_t mel_layout, int64_t batch, int64_t plan, int64_t n_mels, double power,
+                       int64_t max_iter, double tol) {
+  want(mel, at::kFloat, "mel");
+  c10::cuda::CUDAGuard guard(mel.device());
+  mst_batch_t* b = as_batch(batch);
+  TORCH_CHECK(plan != 0, "null mel inverse plan handle");
+  TORCH_CHECK(mst_batch_device(b) == (int)mel.get_device(), "the batch handle lives on another device");
+  TORCH_CHECK(mel.numel() == mst_batch_total_frames(b) * n_mels, "mel has ", mel.numel(), " elements, batch expects ",
+              mst_batch_total_frames(b) * n_mels);
+  at::Tensor S = at::empty({mst_batch_total_frames(b), 1025}, mel.options());
+  check(mst_mel_to_stft_f32(mel.data_ptr<float>(), (int)mel_layout, b, reinterpret_cast<mst_mel_inverse_plan_t*>(plan),
+                            (float)power, (int)max_iter, (float)tol, S.data_ptr<float>(), cur_stream()), "mst_mel_to_stft_f32");
+  return S;
+}
+
 at::Tensor spectral_convergence(const at::Tensor& y, int64_t batch, const at::Tensor& S, int64_t s_layout) {
   want(y, at::kFloat, "y");
   want(S, at::kFloat, "S");
@@ -294,6 +318,8 @@ TORCH_LIBRARY(mst_b200, m) {
   m.def("mel_filterbank(int sr, int n_fft, int n_mels, float fmin, float fmax) -> Tensor", &mel_filterbank);
   m.def("mel_plan_create(Tensor weights, int device) -> int", &mel_plan_create);
   m.def("mel_plan_destroy(int handle) -> ()", &mel_plan_destroy);
+  m.def("mel_inverse_plan_create(Tensor weights, int device) -> int", &mel_inverse_plan_create);
+  m.def("mel_inverse_plan_destroy(int handle) -> ()", &mel_inverse_plan_destroy);
   m.def("launch_count() -> int", &launch_count);
   // device ops: CUDA implementations only
   m.def("stft(Tensor audio, int batch, int out_mode, int layout) -> Tensor");
@@ -311,6 +337,7 @@ TORCH_LIBRARY(mst_b200, m) {
         "int fs, int sr, int pitch_lo, int n_keys, int out_dtype) -> (Tensor, Tensor)");
   m.def("resample(Tensor x, int sr_in, int sr_out) -> Tensor");
   m.def("spectral_convergence(Tensor y, int batch, Tensor S, int s_layout) -> Tensor");
+  m.def("mel_to_stft(Tensor mel, int mel_layout, int batch, int plan, int n_mels, float power, int max_iter, float tol) -> Tensor");
   m.def("griffinlim(Tensor S, int s_layout, bool s_is_log1p_power, int batch, int n_iter, float momentum, "
         "Tensor? init_phase, int init_mode, int seed) -> Tensor");
 }
@@ -327,4 +354,5 @@ TORCH_LIBRARY_IMPL(mst_b200, CUDA, m) {
   m.impl("griffinlim", &griffinlim);
   m.impl("resample", &resample);
   m.impl("spectral_convergence", &spectral_convergence);
+  m.impl("mel_to_stft", &mel_to_stft);
 }

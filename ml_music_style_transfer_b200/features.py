@@ -119,6 +119,26 @@ class MelPlan:
         return cls._cache[key]
 
 
+class MelInversePlan:
+    """Device-resident data of the mel inversion (``mst_mel_inverse_plan_t``): pinv of the filterbank, its sparse
+    column lists and the gradient step, built once per (sr, n_fft, n_mels, fmin, fmax, device)."""
+
+    _cache = {}
+
+    def __init__(self, weights, device):
+        self.n_mels = int(weights.shape[0])
+        self.device = device
+        self.handle = _lib.ops().mel_inverse_plan_create(weights.contiguous(), device.index)
+
+    @classmethod
+    def get(cls, sr, n_fft=N_FFT, n_mels=128, fmin=0.0, fmax=None, device=None):
+        device = _lib.require_cuda(device)
+        key = (int(sr), int(n_fft), int(n_mels), float(fmin), None if fmax is None else float(fmax), device.index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(mel_filterbank(sr, n_fft, n_mels, fmin, fmax), device)
+        return cls._cache[key]
+
+
 def mel_filterbank(sr, n_fft=N_FFT, n_mels=128, fmin=0.0, fmax=None):
     """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False, norm='slaney') -> CPU float32 (n_mels, 1+n_fft/2)."""
     return _lib.ops().mel_filterbank(int(sr), int(n_fft), int(n_mels), float(fmin), 0.0 if fmax is None else float(fmax))
@@ -235,6 +255,50 @@ def griffinlim(S, n_iter=32, hop_length=None, win_length=None, window="hann", mo
     seed = int(np.random.randint(0, 2 ** 31 - 1))
     with ClipBatch.from_frames([T], hop, pad_mode=pad_mode, device=device) as b:
         y = griffinlim_batch(S_flat.to(torch.float32), b, n_iter, momentum, ph, init, seed, layout)
+    return to_numpy(y) if was_np else y
+
+
+def mel_to_stft_batch(M, batch, plan, power=2.0, layout=BIN_MAJOR, max_iter=200, tol=1e-6):
+    """Raw batched op: ``M`` holds every clip's (n_mels x T_c) block in ``layout``; ``batch`` from ClipBatch.from_frames.
+    Returns frame-major magnitudes (total_frames, 1025) -- the form griffinlim_batch consumes in place."""
+    return _lib.ops().mel_to_stft(M.contiguous().view(-1), layout, batch.handle, plan.handle, plan.n_mels, float(power),
+                                  int(max_iter), float(tol))
+
+
+def mel_to_stft(M, sr=22050, n_fft=N_FFT, power=2.0, fmin=0.0, fmax=None, max_iter=200, tol=1e-6):
+    """librosa.feature.inverse.mel_to_stft drop-in: (n_mels, T) mel power spectrogram -> (1025, T) magnitudes
+    ``nnls(mel_basis, M) ** (1 / power)``.  Same start point as librosa.util.nnls (clipped least squares); the NNLS
+    problem of every frame is then solved to ``tol`` (relative residual) instead of stopping where L-BFGS-B's scaled
+    projected-gradient test stops, so the residual ||mel_basis @ S**power - M|| is <= librosa's."""
+    _check_window("hann", None, n_fft)
+    was_np = not isinstance(M, torch.Tensor)
+    device = _lib.require_cuda(None if was_np else M.device)
+    if was_np:
+        M = torch.from_numpy(np.ascontiguousarray(M, dtype=np.float32)).to(device)
+    if M.dim() != 2:
+        raise ValueError(f"M must be (n_mels, T); got {tuple(M.shape)}")
+    n_mels, T = int(M.shape[0]), int(M.shape[1])
+    plan = MelInversePlan.get(sr, n_fft, n_mels, fmin, fmax, device)
+    with ClipBatch.from_frames([T], n_fft // 4, pad_mode="constant", device=device) as b:   # hop is irrelevant here
+        S = mel_to_stft_batch(M.to(torch.float32), b, plan, power, BIN_MAJOR, max_iter, tol)
+    return to_numpy(S).T if was_np else S.t()
+
+
+def mel_to_audio(M, sr=22050, n_fft=N_FFT, hop_length=512, win_length=None, window="hann", center=True, pad_mode="reflect",
+                 power=2.0, n_iter=32, momentum=0.99, init="random", random_state=None, init_phase=None, fmin=0.0, fmax=None):
+    """librosa.feature.inverse.mel_to_audio drop-in (tests/test_griffinlim.py:24, commented in the reference):
+    ``griffinlim(mel_to_stft(M, sr, n_fft, power), n_iter, hop_length, ...)``; the magnitudes never leave the device."""
+    if not center:
+        raise NotImplementedError("center=False is not used by the reference")
+    was_np = not isinstance(M, torch.Tensor)
+    device = _lib.require_cuda(None if was_np else M.device)
+    Md = torch.from_numpy(np.ascontiguousarray(M, dtype=np.float32)).to(device) if was_np else M
+    S = mel_to_stft(Md, sr, n_fft, power, fmin, fmax)        # (1025, T) view of frame-major memory
+    y = griffinlim(S, n_iter=n_iter, hop_length=hop_length, win_length=win_length, window=window, momentum=momentum,
+                   init=init, random_state=random_state,
+                   init_phase=None if init_phase is None else (init_phase if isinstance(init_phase, torch.Tensor) else
+                                                               torch.from_numpy(np.ascontiguousarray(init_phase, dtype=np.float32)).to(device).t().contiguous().t()),
+                   pad_mode=pad_mode)
     return to_numpy(y) if was_np else y
 
 

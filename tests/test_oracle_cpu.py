@@ -91,6 +91,23 @@ def test_mel_filterbank_matches_torchaudio_golden(sr, nnz):
         assert len(idx) >= 2 and idx[-1] - idx[0] + 1 == len(idx)
 
 
+def test_mel_inversion_oracle():
+    """oracle.mel.nnls / mel_to_stft restate librosa.util.nnls + feature.inverse.mel_to_stft: L-BFGS-B from the clipped
+    least-squares point -- feasible, objective not above the start point's, exact on a consistent 1-D problem."""
+    from ml_music_style_transfer_b200 import synth
+    y = synth.piano_clip(5, 0.5, 22050)
+    M = omel.melspectrogram(y, 22050, 2048, 512)
+    W = omel.mel_filterbank(22050, 2048, 128)
+    X0 = np.clip(np.linalg.lstsq(W, M, rcond=None)[0], 0, None)
+    S = omel.mel_to_stft(M, 22050, 2048, power=2.0)
+    assert S.shape == (1025, M.shape[1]) and S.dtype == np.float32 and (S >= 0).all()
+    r = lambda X: np.linalg.norm(W.astype(np.float64) @ X.astype(np.float64) - M)
+    assert r(S.astype(np.float64) ** 2) < r(X0)
+    x_true = np.abs(np.random.default_rng(0).standard_normal(1025)).astype(np.float32)
+    x = omel.nnls(W, W @ x_true)                               # 1-D right-hand side -> scipy.optimize.nnls (active set)
+    assert (x >= 0).all() and np.linalg.norm(W @ x - W @ x_true) < 1e-4 * np.linalg.norm(W @ x_true)
+
+
 def test_c_abi_mel_filterbank_is_bit_exact_with_oracle(built_libs):
     lib = ctypes.CDLL(built_libs[0])
     for sr in (22050, 44100):
