@@ -229,6 +229,41 @@ def test_wav_round_trip_and_load(tmp_path):
 
 
 # ---- host logic --------------------------------------------------------------------------------
+# ---- second, independent pins (tests/golden/make_golden2.py): HuggingFace audio_utils, scipy.signal, closed-form resampler ----
+@pytest.mark.parametrize("sr,hop", [(22050, 512), (44100, 256)])
+def test_oracle_matches_transformers_audio_utils(sr, hop):
+    g = np.load(os.path.join(GOLD, "second_pins.npz"))
+    y = g["y"]
+    assert relerr(omel.mel_filterbank(sr, 2048, 128).astype(np.float64), g[f"hf_fb_{sr}"]) < 2e-6
+    P = np.abs(ostft.stft(y, 2048, hop, out_dtype=np.complex128)) ** 2
+    assert P.shape == g[f"hf_power_{hop}"].shape and relerr(P, g[f"hf_power_{hop}"]) < 1e-6
+    M = omel.melspectrogram(y, sr, 2048, hop)
+    assert M.shape == g[f"hf_mel_{sr}_{hop}"].shape and relerr(M.astype(np.float64), g[f"hf_mel_{sr}_{hop}"]) < 2e-6
+
+
+@pytest.mark.parametrize("hop", [256, 512])
+def test_oracle_matches_scipy_signal(hop):
+    g = np.load(os.path.join(GOLD, "second_pins.npz"))
+    D = ostft.stft(g["y"], 2048, hop)
+    ref = g[f"scipy_stft_{hop}"]
+    assert D.shape == ref.shape and relerr(D, ref) < 3e-7
+    yi = ostft.istft(ref, hop)
+    ri = g[f"scipy_istft_{hop}"]
+    n = min(len(yi), len(ri))
+    assert n >= hop * (ref.shape[1] - 1) - 1
+    assert np.abs(yi[:n] - ri[:n])[1024:-1024].max() < 2e-6   # away from the edge frames, where the two normalise alike
+
+
+@pytest.mark.parametrize("so,sn", [(44100, 22050), (48000, 44100), (22050, 44100)])
+def test_resample_matches_closed_form_full_length(so, sn):
+    """Full-length pin (same zero edge handling): resampy's table + linear interpolation vs the closed-form filter."""
+    g = np.load(os.path.join(GOLD, "second_pins.npz"))
+    y = oaudio.resample(g["rs_x"], so, sn)
+    ref = g[f"rs_direct_{so}_{sn}"]
+    assert y.shape == ref.shape
+    assert np.abs(y - ref).max() < 2e-5 * max(1.0, np.abs(ref).max()), np.abs(y - ref).max()
+
+
 def test_header_symbols_exported(built_libs):
     hdr = open(os.path.join(ROOT, "include", "mst_b200.h")).read()
     names = sorted(set(re.findall(r"\b(mst_[a-z0-9_]+)\s*\(", hdr)))
