@@ -225,6 +225,9 @@ int mst_spectral_convergence_f32(const float* d_y, const mst_batch_t* batch, con
  * ------------------------------------------------------------------------------------------- */
 int64_t mst_resample_length(int64_t n_in, int sr_in, int sr_out);
 int mst_resample_f32(const float* d_in, int64_t n_in, int sr_in, int sr_out, float* d_out, mst_stream_t stream);
+/* librosa.to_mono (np.mean over channels, float32) of the interleaved frames a WAV file stores: d_out[t] =
+ * (sum_c d_interleaved[t * channels + c]) / channels. */
+int mst_mono_mix_f32(const float* d_interleaved, int64_t n_frames, int channels, float* d_out, mst_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -63,7 +63,7 @@ def load(path, sr=22050, as_numpy=True, device=None):
     x, sr_native = read_wav(path)
     device = _lib.require_cuda(device)
     t = torch.from_numpy(x).to(device)
-    y = t.mean(dim=1) if t.shape[1] > 1 else t[:, 0].contiguous()
+    y = _lib.ops().mono_mix(t.contiguous()) if t.shape[1] > 1 else t[:, 0].contiguous()   # librosa.to_mono
     if sr is not None and sr != sr_native:
         y = _lib.ops().resample(y.contiguous(), int(sr_native), int(sr))
         sr_native = sr

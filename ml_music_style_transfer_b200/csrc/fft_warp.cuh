@@ -292,6 +292,22 @@ __device__ __forceinline__ float fast_log1p(float x) {
   return x < 0.25f ? small : big;
 }
 
+// The same for two values at once with packed fp32x2 arithmetic (the two special-function lookups per value stay
+// scalar): 9.5 issue slots per value instead of 16; the same formula per component.
+__device__ __forceinline__ float2 fast_log1p2(float2 x) {
+  const float2 den = pk_add(x, pk_bcast(2.0f));
+  const float2 s = pk_mul(x, make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y)));
+  const float2 s2 = pk_mul(s, s);
+  float2 poly = pk_fma(s2, pk_bcast(1.0f / 9.0f), pk_bcast(1.0f / 7.0f));
+  poly = pk_fma(s2, poly, pk_bcast(0.2f));
+  poly = pk_fma(s2, poly, pk_bcast(1.0f / 3.0f));
+  poly = pk_fma(s2, poly, pk_bcast(1.0f));
+  const float2 small = pk_mul(pk_mul(pk_bcast(2.0f), s), poly);
+  const float2 u = pk_add(x, pk_bcast(1.0f));
+  const float2 big = pk_mul(make_float2(__log2f(u.x), __log2f(u.y)), pk_bcast(0.69314718055994530942f));
+  return make_float2(x.x < 0.25f ? small.x : big.x, x.y < 0.25f ? small.y : big.y);
+}
+
 // Cooperative copy of a 16-byte-aligned table into shared memory (n_vec4 float4 elements).
 __device__ __forceinline__ void stage_table(void* dst, const void* src, int n_vec4) {
   const float4* a = reinterpret_cast<const float4*>(src);

@@ -2,8 +2,8 @@
 // (reference preprocessing/preprocess.py:106, model/inference.py:54, tests/test_griffinlim.py:16).
 // Band-limited sinc interpolation exactly as resampy 0.2.2 'kaiser_best' evaluates it (librosa 0.8's default
 // res_type): half-window rolloff*sinc(rolloff*t)*kaiser(beta) tabulated 512 times per zero crossing over 64 zero
-// crossings, linear interpolation between table entries, left wing then right wing.  One thread per output sample;
-// the 256 KB (value, delta) table is L2 resident.  Index arithmetic is done in double so that table offsets match
+// crossings, linear interpolation between table entries, left wing then right wing.  General ratios: one thread per
+// output sample, the 256 KB (value, delta) table L2 resident; exact halving of the rate takes resample_half_kernel.  Index arithmetic is done in double so that table offsets match
 // the Python evaluation bit for bit.
 #include <math.h>
 #include <map>
@@ -51,6 +51,69 @@ __global__ void resample_kernel(const float* __restrict__ x, int64_t n_in, float
       acc = fmaf(fmaf(eta, w.y, w.x), __ldg(x + n + k + 1), acc);
     }
     y[t] = acc;
+  }
+}
+
+// Decimation by exactly 2 (44.1 -> 22.05 kHz, 48 -> 24 kHz ...): time_increment is the integer 2, so every output has
+// the SAME table phase (offset 0 / eta 0 on the left wing, offset 256 / eta 0 on the right) and resampy's two wings
+// collapse into one symmetric 255-tap FIR  y[t] = sum_{d=-127}^{127} c_|d| x[2t + d],  c_k = table[256 k]  (the wing
+// limits (32769 - offset) / 256 give 128 left and 127 right taps; beyond the signal the wings stop, i.e. zero padding).
+// A CTA of 128 threads stages its input span in shared memory split into even and odd samples (so that consecutive
+// lanes read consecutive words), keeps the 128 coefficients there too (broadcast reads), and every thread accumulates
+// 4 outputs at once: 1 coefficient load + 4 sample loads + 4 FMAs per tap instead of 2 global loads + index arithmetic
+// per tap and output.
+constexpr int kHalfThreads = 128, kHalfPerThread = 4, kHalfOut = kHalfThreads * kHalfPerThread;  // 512 outputs per CTA
+constexpr int kHalfSpan = kHalfOut + 128;                                                       // even / odd samples staged
+
+__global__ void __launch_bounds__(kHalfThreads)
+resample_half_kernel(const float* __restrict__ x, int64_t n_in, float* __restrict__ y, int64_t n_out, int64_t n_fix,
+                     const float2* __restrict__ table) {
+  __shared__ float s_c[128];
+  __shared__ float s_e[kHalfSpan], s_o[kHalfSpan];
+  const int tid = threadIdx.x;
+  s_c[tid] = __ldg(table + tid * 256).x;
+  for (int64_t T0 = (int64_t)blockIdx.x * kHalfOut; T0 < n_fix; T0 += (int64_t)gridDim.x * kHalfOut) {
+    __syncthreads();
+    for (int i = tid; i < kHalfSpan; i += kHalfThreads) {   // s_e[i] = x[2 (T0 - 64 + i)], s_o[i] = x[2 (T0 - 64 + i) + 1]
+      const int64_t m = 2 * (T0 - 64 + i);
+      s_e[i] = (m >= 0 && m < n_in) ? __ldg(x + m) : 0.0f;
+      s_o[i] = (m + 1 >= 0 && m + 1 < n_in) ? __ldg(x + m + 1) : 0.0f;
+    }
+    __syncthreads();
+    float acc[kHalfPerThread];
+#pragma unroll
+    for (int q = 0; q < kHalfPerThread; ++q) acc[q] = 0.0f;
+    // even taps d = 2e, e = -63..63: x[2t + 2e] = s_e[(t - T0) + 64 + e]
+#pragma unroll 4
+    for (int e = -63; e <= 63; ++e) {
+      const float c = s_c[e < 0 ? -2 * e : 2 * e];
+#pragma unroll
+      for (int q = 0; q < kHalfPerThread; ++q) acc[q] = fmaf(c, s_e[tid + kHalfThreads * q + 64 + e], acc[q]);
+    }
+    // odd taps d = 2e + 1, e = -64..63: x[2t + 2e + 1] = s_o[(t - T0) + 64 + e]
+#pragma unroll 4
+    for (int e = -64; e <= 63; ++e) {
+      const int d = 2 * e + 1;
+      const float c = s_c[d < 0 ? -d : d];
+#pragma unroll
+      for (int q = 0; q < kHalfPerThread; ++q) acc[q] = fmaf(c, s_o[tid + kHalfThreads * q + 64 + e], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < kHalfPerThread; ++q) {
+      const int64_t t = T0 + tid + kHalfThreads * q;
+      if (t < n_fix) y[t] = t < n_out ? acc[q] : 0.0f;   // fix_length: zero padding up to ceil(n / 2)
+    }
+  }
+}
+
+// librosa.to_mono = np.mean(y, axis=0) on the decoded (channels, n) array: float32 sum over channels in channel order,
+// divided by the channel count.  Input here is the interleaved frame layout a WAV file stores.
+__global__ void mono_mix_kernel(const float* __restrict__ interleaved, int64_t n_frames, int channels, float* __restrict__ y) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_frames; t += (int64_t)gridDim.x * blockDim.x) {
+    const float* f = interleaved + t * channels;
+    float acc = f[0];
+    for (int c = 1; c < channels; ++c) acc += f[c];
+    y[t] = __fdiv_rn(acc, (float)channels);
   }
 }
 
@@ -113,6 +176,18 @@ int64_t mst_resample_length(int64_t n_in, int sr_in, int sr_out) {
   return (int64_t)ceil((double)n_in * ((double)sr_out / (double)sr_in));
 }
 
+int mst_mono_mix_f32(const float* d_interleaved, int64_t n_frames, int channels, float* d_out, mst_stream_t stream) {
+  if (!d_interleaved || !d_out) return fail(MST_ERR_INVALID, "mst_mono_mix_f32: null argument");
+  if (n_frames < 0 || channels < 1) return fail(MST_ERR_INVALID, "mst_mono_mix_f32: bad sizes");
+  if (n_frames == 0) return MST_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t blocks = (n_frames + 255) / 256;
+  mono_mix_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, s>>>(d_interleaved, n_frames, channels, d_out);
+  MST_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return MST_OK;
+}
+
 int mst_resample_f32(const float* d_in, int64_t n_in, int sr_in, int sr_out, float* d_out, mst_stream_t stream) {
   if (!d_in || !d_out) return fail(MST_ERR_INVALID, "mst_resample_f32: null argument");
   if (n_in <= 0 || sr_in <= 0 || sr_out <= 0) return fail(MST_ERR_INVALID, "mst_resample_f32: bad sizes");
@@ -130,6 +205,13 @@ int mst_resample_f32(const float* d_in, int64_t n_in, int sr_in, int sr_out, flo
   const float2* table = nullptr;
   int rc = get_rs_table(sr_in, sr_out, &table);
   if (rc) return rc;
+  if (sr_in == 2 * sr_out) {  // one table phase for every output: the symmetric-FIR decimator
+    const int64_t ctas = (n_fix + kHalfOut - 1) / kHalfOut;
+    resample_half_kernel<<<(unsigned)(ctas < 148 * 16 ? ctas : 148 * 16), kHalfThreads, 0, s>>>(d_in, n_in, d_out, n_out, n_fix, table);
+    MST_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return MST_OK;
+  }
   const int threads = 256;
   const int64_t blocks = (n_fix + threads - 1) / threads;
   resample_kernel<<<(unsigned)(blocks < 148 * 64 ? blocks : 148 * 64), threads, 0, s>>>(d_in, n_in, d_out, n_out, n_fix, table,

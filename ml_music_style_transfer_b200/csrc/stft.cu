@@ -16,9 +16,12 @@ namespace mst {
 
 constexpr int kModeConv = 5;          // internal epilogue: per-clip sums of (|S| - S_target)^2 and S_target^2 (spectral convergence)
 constexpr int kModeSplit = 4;         // internal epilogue: |S|^2 as split bf16 (hi, lo) rows for the tensor-core mel projection
-constexpr int kRowsPerWarp = 32 / kWarpsPerCta;       // bin rows one warp stores per trip of the bin-major epilogue (3 at 10 warps)
-constexpr int kTileStride = 1024 + kRowsPerWarp;     // floats per frame row of the bin-major staging tile: bank = (stride * f + k) % 32 is
-                                                       // distinct over the (frame, row) pairs of a warp -> conflict-free reads
+// Bin-major staging: every warp parks its frame's 1025 epilogue values inside ITS OWN scratch tile (so no barrier is
+// needed between the FFT and the parking), row f starting 4 f floats into the tile: with a row pitch of 2112 floats
+// (== 0 mod 32) the shift makes bank = (4 f + k) % 32 distinct over the 8 frames x 4 bins one warp reads per trip.
+constexpr int kTileStride = 2 * kScratchPerWarp + 4;   // floats from row f to row f + 1 (scratch pitch + the 4-float shift)
+static_assert(kWarpsPerCta == 8, "the bin-major epilogue maps 32 lanes to 8 frames x 4 bins");
+static_assert(kBins + 4 * (kWarpsPerCta - 1) <= 2 * kScratchPerWarp, "staging row must fit the warp's scratch tile");
 
 struct SplitOut {          // ring of split-precision power-spectrum rows (kSpecPad bf16 each), consumed by mel_gemm.cu
   __nv_bfloat16* hi;
@@ -69,6 +72,15 @@ __device__ __forceinline__ float epilogue_value(float2 x) {
   const float p = fmaf(x.x, x.x, x.y * x.y);
   if (MODE == MST_OUT_MAGNITUDE) return sqrtf(p);
   if (MODE == MST_OUT_LOG1P_POWER) return fast_log1p(p);
+  return p;
+}
+
+// Epilogue of two bins at once (packed arithmetic where the operation allows it).
+template <int MODE>
+__device__ __forceinline__ float2 epilogue_pair(float2 a, float2 b) {
+  const float2 p = make_float2(fmaf(a.x, a.x, a.y * a.y), fmaf(b.x, b.x, b.y * b.y));
+  if (MODE == MST_OUT_MAGNITUDE) return make_float2(sqrtf(p.x), sqrtf(p.y));
+  if (MODE == MST_OUT_LOG1P_POWER) return fast_log1p2(p);
   return p;
 }
 
@@ -209,28 +221,46 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
         if (active) {
           float* row = out + g * kBins;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) row[mirror_bin(lane, kb, j)] = epilogue_value<MODE>(o[j]);
+          for (int j = 0; j < 32; j += 2) {
+            const float2 e = epilogue_pair<MODE>(o[j], o[j + 1]);
+            row[mirror_bin(lane, kb, j)] = e.x;
+            row[mirror_bin(lane, kb, j + 1)] = e.y;
+          }
           if (lane == 0) row[512] = epilogue_value<MODE>(mid);
         }
       } else {
-        __syncthreads();
+        __syncwarp();  // this warp is done with its scratch tile (split butterflies read registers only)
         if (active) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s_tile[warp * kTileStride + mirror_bin(lane, kb, j)] = epilogue_value<MODE>(o[j]);
+          for (int j = 0; j < 32; j += 2) {
+            const float2 e = epilogue_pair<MODE>(o[j], o[j + 1]);
+            s_tile[warp * kTileStride + mirror_bin(lane, kb, j)] = e.x;
+            s_tile[warp * kTileStride + mirror_bin(lane, kb, j + 1)] = e.y;
+          }
           if (lane == 0) s_tile[warp * kTileStride + 512] = epilogue_value<MODE>(mid);
         }
       }
     }
     if (layout == MST_LAYOUT_BIN_MAJOR) {
-      // transposed store: clip block is [n_out][T]; the tile's consecutive frames give one contiguous segment per bin row,
-      // a warp stores kRowsPerWarp rows per trip (lane = (row, frame))
+      // transposed store: clip block is [n_out][T]; the tile's 8 consecutive frames give one 32-byte segment per bin row
       __syncthreads();
       const int nvalid = min(kWarpsPerCta, cd.frames - t0);
-      const int f = lane % kWarpsPerCta, rr = lane / kWarpsPerCta;
       float* blk = out + cd.frame_offset * n_out;
-      if (rr < kRowsPerWarp && f < nvalid) {
-        for (int k = warp * kRowsPerWarp + rr; k < n_out; k += kRowsPerWarp * kWarpsPerCta)
-          blk[(int64_t)k * cd.frames + t0 + f] = s_tile[f * kTileStride + k];
+      const bool vec4 = (cd.frames & 3) == 0 && ((cd.frame_offset * n_out) & 3) == 0 && nvalid == kWarpsPerCta &&
+                        (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+      if (vec4) {
+        // T % 4 == 0 (e.g. the reference's 860-frame chunks): every row segment is two aligned float4 stores
+        const int h = threadIdx.x & 1;
+        for (int k = threadIdx.x >> 1; k < n_out; k += kWarpsPerCta * 16) {
+          const float* sp = s_tile + (4 * h) * kTileStride + k;
+          const float4 v = make_float4(sp[0], sp[kTileStride], sp[2 * kTileStride], sp[3 * kTileStride]);
+          *reinterpret_cast<float4*>(blk + (int64_t)k * cd.frames + t0 + 4 * h) = v;
+        }
+      } else {
+        const int f = threadIdx.x & 7, kk = threadIdx.x >> 3;
+        if (f < nvalid) {
+          for (int k = kk; k < n_out; k += 32) blk[(int64_t)k * cd.frames + t0 + f] = s_tile[f * kTileStride + k];
+        }
       }
       __syncthreads();
     }

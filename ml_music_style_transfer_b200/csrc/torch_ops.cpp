@@ -305,6 +305,16 @@ at::Tensor resample(const at::Tensor& x, int64_t sr_in, int64_t sr_out) {
   return y;
 }
 
+at::Tensor mono_mix(const at::Tensor& frames) {
+  want(frames, at::kFloat, "frames");
+  TORCH_CHECK(frames.dim() == 2, "mono_mix expects (n_frames, channels) interleaved samples");
+  c10::cuda::CUDAGuard guard(frames.device());
+  at::Tensor y = at::empty({frames.size(0)}, frames.options());
+  check(mst_mono_mix_f32(frames.data_ptr<float>(), frames.size(0), (int)frames.size(1), y.data_ptr<float>(), cur_stream()),
+        "mst_mono_mix_f32");
+  return y;
+}
+
 }  // namespace
 
 TORCH_LIBRARY(mst_b200, m) {
@@ -336,6 +346,7 @@ TORCH_LIBRARY(mst_b200, m) {
   m.def("pianoroll_upsample_pair(Tensor roll, Tensor onoff, Tensor row_offsets, Tensor sample_offsets, int total_samples, "
         "int fs, int sr, int pitch_lo, int n_keys, int out_dtype) -> (Tensor, Tensor)");
   m.def("resample(Tensor x, int sr_in, int sr_out) -> Tensor");
+  m.def("mono_mix(Tensor frames) -> Tensor");
   m.def("spectral_convergence(Tensor y, int batch, Tensor S, int s_layout) -> Tensor");
   m.def("mel_to_stft(Tensor mel, int mel_layout, int batch, int plan, int n_mels, float power, int max_iter, float tol) -> Tensor");
   m.def("griffinlim(Tensor S, int s_layout, bool s_is_log1p_power, int batch, int n_iter, float momentum, "
@@ -353,6 +364,7 @@ TORCH_LIBRARY_IMPL(mst_b200, CUDA, m) {
   m.impl("pianoroll_upsample_pair", &pianoroll_upsample_pair);
   m.impl("griffinlim", &griffinlim);
   m.impl("resample", &resample);
+  m.impl("mono_mix", &mono_mix);
   m.impl("spectral_convergence", &spectral_convergence);
   m.impl("mel_to_stft", &mel_to_stft);
 }

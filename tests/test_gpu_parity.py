@@ -416,6 +416,20 @@ def test_resample_kaiser_best(pkg, so, sn):
     assert_close(got, ref.astype(np.float64))
 
 
+def test_resample_halving_edge_cases_and_mono_mix(pkg, gpu):
+    """The decimate-by-2 FIR path (one table phase for every output) at awkward lengths, and librosa.to_mono."""
+    for n in (2, 3, 100, 255, 1023, 4097):   # (n = 1 gives zero output samples: resampy itself raises there)
+        x = clip(55, max(n, 1025), "noise")[:n] * 3.0
+        got = pkg.audio_io.resample(x, 44100, 22050)
+        ref = oaudio.resample(x, 44100, 22050)
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), (n, np.abs(got - ref).max())
+    for ch in (2, 3, 6):
+        fr = np.random.default_rng(ch).standard_normal((1000, ch)).astype(np.float32)
+        mono = pkg._lib.ops().mono_mix(torch.from_numpy(fr).to(gpu)).cpu().numpy()
+        assert np.array_equal(mono, np.mean(fr.T, axis=0))
+
+
 def test_load_audio_dropin(pkg, tmp_path):
     """preprocess.py:99-115 on a stereo 48 kHz PCM16 file -> mono float32 at hp.sr = 44100."""
     x = np.stack([clip(53, 24000), clip(54, 24000, "noise")], axis=1)

@@ -12,7 +12,7 @@ import bench  # noqa: E402
 from ml_music_style_transfer_b200 import features as F, pianoroll as PR  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-stages = sys.argv[2:] or ["mel", "logpower", "gl", "roll"]
+stages = sys.argv[2:] or ["mel", "logpower", "gl", "roll"]   # also: logpower_bm (bin-major), repo (reference geometry, T = 860)
 dev = torch.device("cuda", 0)
 audio = bench.make_audio_device(n, dev, 0)
 batch = F.ClipBatch.uniform(n, bench.CLIP_LEN, bench.HOP, device=dev)
@@ -25,6 +25,15 @@ for rep in range(3):
         F.melspectrogram_batch(audio, batch, plan, log1p=True, layout=F.BIN_MAJOR)
     if "logpower" in stages:
         F.stft_batch(audio, batch, "log1p_power", F.FRAME_MAJOR)
+    if "logpower_bm" in stages:
+        F.stft_batch(audio, batch, "log1p_power", F.BIN_MAJOR)
+    if "repo" in stages:
+        if rep == 0:
+            n_ch, step_, clen = 256, 131072, 219904
+            a_repo = torch.randn((n_ch - 1) * step_ + clen, device=dev) * 0.1
+            b_repo = F.ClipBatch.uniform(n_ch, clen, 256, clip_stride=step_, device=dev)
+        F.stft_batch(a_repo, b_repo, "log1p_power", F.BIN_MAJOR)
+        F.stft_batch(a_repo, b_repo, "log1p_power", F.FRAME_MAJOR)
     if "gl" in stages:
         F.griffinlim_batch(S, gl_batch, n_iter=4, seed=1, layout=F.FRAME_MAJOR)
     if "roll" in stages:
