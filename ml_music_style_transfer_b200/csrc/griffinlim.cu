@@ -55,12 +55,15 @@ struct GlParams {
 };
 
 __device__ __forceinline__ float uniform_hash(unsigned long long seed, unsigned long long idx) {
-  // splitmix64 -> 24-bit mantissa uniform in [0,1)
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
+  // counter-based generator for the random initial phase (librosa draws it from NumPy's global RNG, i.e. it is
+  // unspecified): two rounds of 32-bit multiply-xorshift mixing (murmur3 / "lowbias32" finalisers) over the 64-bit element
+  // index and the seed -> 24-bit mantissa uniform in [0,1).  All 32-bit: 64-bit multiplies cost 4-6 IMADs each and the
+  // initial-synthesis launch was spending more time here than a full iteration does.
+  unsigned x = (unsigned)idx * 0x9E3779B1u ^ ((unsigned)(idx >> 32) + 0x7F4A7C15u) * 0x85EBCA77u ^ (unsigned)seed;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  x += (unsigned)(seed >> 32) * 0x27D4EB2Fu + 0x165667B1u;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
 }
 
 // Inverse transform of one frame's spectrum (mirror layout), synthesis window (1/1024 folded in), and park the 2048
@@ -228,7 +231,15 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
       float2 y[32];
       float2 mid = make_float2(0.0f, 0.0f);
       if (INIT) {
-        // y_0 = istft(S * exp(2*pi*i*u))
+        // y_0 = istft(S * exp(2*pi*i*u)).  All target magnitudes are requested first (33 loads in flight per lane), the
+        // phases are computed while they arrive: the one-load-one-use form left a DRAM round trip exposed per bin
+        // (ncu: long_scoreboard 5.7 cycles per issued instruction in this launch).
+        float s_in[33];
+#pragma unroll
+        for (int j = 0; j < 33; ++j) {
+          if (j == 32 && lane != 0) break;
+          s_in[j] = ld_stream(Srow + (j < 32 ? mirror_bin(lane, kb, j) : 512));
+        }
 #pragma unroll
         for (int j = 0; j < 33; ++j) {
           if (j == 32 && lane != 0) break;
@@ -248,8 +259,7 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
             const float turns = u - rintf(u);
             __sincosf(6.283185307179586f * turns, &sn, &cs);
           }
-          const float s = ld_stream(Srow + k);
-          const float2 val = make_float2(s * cs, s * sn);
+          const float2 val = pk_mul(pk_bcast(s_in[j]), make_float2(cs, sn));
           if (j < 32) y[j] = val; else mid = val;
         }
       } else {

@@ -250,8 +250,12 @@ __device__ __forceinline__ uint4 splat_vector(int8_t v) {
   return *reinterpret_cast<const uint4*>(vals);
 }
 
+// 4 CTAs x 256 threads per SM (<= 64 registers): the kernel waits on its two staged byte loads per chunk (ncu: 60 % of the
+// stall samples), so resident warps are what hides them.  Measured at 4096 clips (profiles/r2_ab_upsample.log): no cap
+// (78 registers, 3 CTAs) 5.31 TB/s; cap 4: 5.80; cap 5 / 6 / 8 (spills): 5.61 / 5.54 / 4.76; prefetching the next chunk's
+// bytes before the stores of the current one: 5.57 with the cap, 4.91 without -- the cap alone wins.
 template <typename OUT, int NP>
-__global__ void __launch_bounds__(256) upsample_kernel(const int8_t* __restrict__ plane0, const int8_t* __restrict__ plane1,
+__global__ void __launch_bounds__(256, 4) upsample_kernel(const int8_t* __restrict__ plane0, const int8_t* __restrict__ plane1,
                                                        const int64_t* __restrict__ row_off, const int64_t* __restrict__ samp_off,
                                                        int n_pieces, int fs, int sr, int pitch_lo, int n_keys,
                                                        OUT* __restrict__ out0, OUT* __restrict__ out1) {
@@ -520,7 +524,8 @@ static int launch_upsample(const void* d_plane0, const void* d_plane1, const int
   const int64_t avg = total_samples / n_pieces + 1;
   const int epv = out_dtype == MST_DTYPE_I8 ? 16 : 4;
   const int64_t chunks = (avg / epv + 32 * kUpVec - 1) / (32 * kUpVec);  // warp-chunks per key row (average piece)
-  // each CTA (8 warps) walks >= 4 rounds of chunks of its row when the grid is large enough to fill the GPU anyway
+  // each CTA (8 warps) walks up to 4 rounds of chunks of its row when the grid is large enough to fill the GPU anyway
+  // (measured: 4 / 8 / 16 / 32 / 64 chunks per CTA -> 3.7 / 4.5 / 5.0 / 5.3 / 5.3 TB/s)
   const int64_t rows = (int64_t)n_keys * n_pieces;
   int64_t per_cta = rows >= 8 * 148 ? 32 : 8;
   const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (chunks + per_cta - 1) / per_cta));

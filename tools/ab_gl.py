@@ -38,6 +38,18 @@ t32 = timed(lambda: F.griffinlim_batch(S, gb, n_iter=32, seed=1, layout=F.FRAME_
 tm = timed(lambda: F.melspectrogram_batch(audio, batch, plan, log1p=True, layout=F.BIN_MAJOR))
 tp = timed(lambda: F.stft_batch(audio, batch, "log1p_power", F.FRAME_MAJOR))
 tb = timed(lambda: F.stft_batch(audio, batch, "log1p_power", F.BIN_MAJOR))
+from ml_music_style_transfer_b200 import pianoroll as PR  # noqa: E402
+notes = PR.NoteBatch(*bench.make_notes(n, 99), device=dev)
+roll, onoff, row_off, _ = PR.rasterize(notes, bench.ROLL_FS)
+
+
+def up():
+    for s0 in range(0, n, 1024):
+        PR.upsample_pair(roll, onoff, row_off[s0:min(n, s0 + 1024) + 1], bench.CLIP_LEN, bench.ROLL_FS, bench.SR, 21, 88, torch.int8)
+
+
+tu = timed(up)
 print(f"{os.environ.get('LD_PRELOAD', 'default').split('/')[-2] if os.environ.get('LD_PRELOAD') else 'default':8s} clips {n}: "
       f"GL iteration {(t32 - t0) / 32:.3f} ms (x{16384 / n:.0f} = {(t32 - t0) / 32 * 16384 / n:.2f} ms @16384), GL-32 {t32:.1f} ms, "
-      f"log-mel {tm:.3f} ms, log1p-power frame-major {tp:.3f} ms, bin-major {tb:.3f} ms", flush=True)
+      f"log-mel {tm:.3f} ms, log1p-power frame-major {tp:.3f} ms, bin-major {tb:.3f} ms, GL init+final {t0:.2f} ms, "
+      f"upsample pair {tu:.2f} ms = {2 * n * 88 * bench.CLIP_LEN / tu / 1e6:.0f} GB/s", flush=True)

@@ -92,6 +92,6 @@ if traffic:
     n_clips = int(os.environ.get("PROF_CLIPS", "1024"))
     tj = {"source": f"ncu --set full, gl_kernel<false,false>, {n_clips} clips x 173 frames (profiles/{tag}_ncu_full_summary.csv)",
           "gl_iteration_dram_bytes_per_clip": (traffic["dram_bytes_read"] + traffic["dram_bytes_write"]) / n_clips, **traffic}
-    with open(os.path.join(out_dir, "traffic.json"), "w") as f:
+    with open(os.path.join(out_dir, f"{tag}_traffic_smallbatch.json"), "w") as f:  # traffic.json itself comes from the bench-size capture
         json.dump(tj, f, indent=1)
 print("wrote", sorted(os.listdir(out_dir)))
