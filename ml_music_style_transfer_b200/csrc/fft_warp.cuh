@@ -83,9 +83,15 @@ __device__ __forceinline__ float2 pk_mul(float2 a, float2 b) { return make_float
 __device__ __forceinline__ float2 pk_bcast(float s) { return make_float2(s, s); }
 __device__ __forceinline__ float2 pk_neg(float2 a) { return make_float2(-a.x, -a.y); }
 
-// a * b (complex):  (a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x) as  a.x * b + a.y * (-b.y, b.x)
+// a * b (complex):  (a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x) = a.x * b + a.y * (-b.y, b.x).  The half-swapped,
+// half-negated pair must be the FIRST operand of the FFMA2: there ptxas folds swap and sign into operand modifiers
+// (-R4.F32x2.LO_HI.NP); as second operand, or in an FMUL2, it is materialised with extra FADD / MOV instructions.
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return pk_fma(pk_bcast(a.x), b, pk_mul(pk_bcast(a.y), make_float2(-b.y, b.x)));
+  return pk_fma(make_float2(-b.y, b.x), pk_bcast(a.y), pk_mul(pk_bcast(a.x), b));
+}
+// a * conj(b):  (a.x*b.x + a.y*b.y, -a.x*b.y + a.y*b.x) = a.x * (b.x, -b.y) + a.y * (b.y, b.x)
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {
+  return pk_fma(make_float2(b.x, -b.y), pk_bcast(a.x), pk_mul(pk_bcast(a.y), make_float2(b.y, b.x)));
 }
 
 // One radix-2 decimation-in-time butterfly with the compile-time twiddle w = W_32^Q (forward) / conj (inverse):
@@ -154,9 +160,8 @@ __device__ __forceinline__ void fft1024_front(float2 (&v)[32], float2* scratch, 
   for (int k1 = 0; k1 < 32; ++k1) {
     float2 a = v[br5(k1)];
     if (k1 != 0) {
-      float2 w = tw[k1 * 32 + lane];
-      if (SIGN > 0) w.y = -w.y;
-      a = cmul(a, w);
+      const float2 w = tw[k1 * 32 + lane];
+      a = SIGN > 0 ? cmul_conj(a, w) : cmul(a, w);
     }
     scratch[k1 * 33 + lane] = a;
   }
@@ -185,9 +190,8 @@ __device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* scratch, c
       for (int k1 = 0; k1 < 32; ++k1) {
         float2 a = v[br5(k1)];
         if (k1 != 0) {
-          float2 w = tw[k1 * 32 + lane];
-          if (SIGN > 0) w.y = -w.y;
-          a = cmul(a, w);
+          const float2 w = tw[k1 * 32 + lane];
+          a = SIGN > 0 ? cmul_conj(a, w) : cmul(a, w);
         }
         scratch[k1 * 33 + lane] = a;
       }
@@ -214,13 +218,14 @@ __device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* scratch, c
 __device__ __forceinline__ int mirror_base(int lane) { return lane == 0 ? 32 : 32 - lane; }
 __device__ __forceinline__ int mirror_bin(int lane, int kb, int j) { return j < 16 ? lane + 32 * j : kb + 32 * j; }
 
-// One pair butterfly.  z = value at bin k, p = value at bin 1024-k, w = -0.5i*exp(-2*pi*i*k/2048) (conjugated by the
-// caller for the inverse direction).  Returns out_k = 0.5*(z + conj p) + w*(z - conj p) and
+// One pair butterfly.  z = value at bin k, p = value at bin 1024-k, w = -0.5i*exp(-2*pi*i*k/2048) (CONJ_W: its conjugate,
+// the inverse direction).  Returns out_k = 0.5*(z + conj p) + w*(z - conj p) and
 // out_m = conj(0.5*(z + conj p) - w*(z - conj p)).
+template <bool CONJ_W>
 __device__ __forceinline__ void pair_butterfly(float2 z, float2 p, float2 w, float2& out_k, float2& out_m) {
   const float2 s = pk_add(z, make_float2(p.x, -p.y));   // z + conj p
   const float2 d = pk_add(z, make_float2(-p.x, p.y));   // z - conj p
-  const float2 t = pk_fma(pk_bcast(w.x), d, pk_mul(pk_bcast(w.y), make_float2(-d.y, d.x)));  // w * d
+  const float2 t = CONJ_W ? cmul_conj(d, w) : cmul(d, w);   // w * d  (conj(w) * d for the inverse direction)
   out_k = pk_fma(pk_bcast(0.5f), s, t);
   out_m = pk_fma(make_float2(0.5f, -0.5f), s, make_float2(-t.x, t.y));
 }
@@ -237,12 +242,12 @@ __device__ __forceinline__ void rfft_split(float2 (&v)[32], float2 (&o)[32], flo
     p.x = __shfl_sync(MST_FULL_MASK, v[br5(31 - r)].x, src);
     p.y = __shfl_sync(MST_FULL_MASK, v[br5(31 - r)].y, src);
     if (lane == 0) p = v[br5((32 - r) & 31)];  // lane 0 pairs with itself: bin 32*r <-> bin 32*(32-r); r = 0 -> Z[0]
-    pair_butterfly(z, p, twp[lane + 32 * r], o[r], o[31 - r]);
+    pair_butterfly<false>(z, p, twp[lane + 32 * r], o[r], o[31 - r]);
   }
   {
     const float2 z = v[br5(16)];  // lane 0: Z[512], its own partner
     float2 dummy;
-    pair_butterfly(z, z, twp[512], *mid, dummy);
+    pair_butterfly<false>(z, z, twp[512], *mid, dummy);
   }
 }
 
@@ -263,9 +268,7 @@ __device__ __forceinline__ void irfft2048_warp(float2 (&y)[32], float2 mid, floa
   for (int r = 0; r < 16; ++r) {
     float2 a = y[r], b = y[31 - r];
     if (r == 0 && lane == 0) { a.y = 0.0f; b.y = 0.0f; }  // DC / Nyquist
-    float2 w = twp[lane + 32 * r];
-    w.y = -w.y;
-    pair_butterfly(a, b, w, v[r], t[r]);
+    pair_butterfly<true>(a, b, twp[lane + 32 * r], v[r], t[r]);
   }
 #pragma unroll
   for (int r = 0; r < 16; ++r) {

@@ -14,7 +14,10 @@ constexpr int kHalf = kNfft / 2;      // complex FFT length (even/odd packing) a
 // Warps (= frames of one tile) per CTA.  8 warps x 2 CTAs = 16 resident warps per SM at 128 registers per thread.  Measured
 // alternative (round 2): 10 warps x 2 CTAs = 20 warps at 96 registers (36-88 B of spills, 221 KB of shared memory so the L1
 // shrinks to its minimum): Griffin-Lim iteration 19.7 ms vs 18.75 ms, log-mel 14.4 vs 13.7 ms -- slower, so 8 it stays.
-constexpr int kWarpsPerCta = 8;
+#ifndef MST_WARPS_PER_CTA
+#define MST_WARPS_PER_CTA 8
+#endif
+constexpr int kWarpsPerCta = MST_WARPS_PER_CTA;
 constexpr int kScratchPerWarp = 32 * 33;  // float2 elements: padded 32x32 transpose tile == one 2048-sample frame slot
 
 // ---- error plumbing -----------------------------------------------------------------------

@@ -20,7 +20,7 @@ constexpr int kModeSplit = 4;         // internal epilogue: |S|^2 as split bf16 
 // needed between the FFT and the parking), row f starting 4 f floats into the tile: with a row pitch of 2112 floats
 // (== 0 mod 32) the shift makes bank = (4 f + k) % 32 distinct over the 8 frames x 4 bins one warp reads per trip.
 constexpr int kTileStride = 2 * kScratchPerWarp + 4;   // floats from row f to row f + 1 (scratch pitch + the 4-float shift)
-static_assert(kWarpsPerCta == 8, "the bin-major epilogue maps 32 lanes to 8 frames x 4 bins");
+// (the bin-major epilogue below maps 32 lanes to 8 frames x 4 bins: builds with another tile size refuse that layout)
 static_assert(kBins + 4 * (kWarpsPerCta - 1) <= 2 * kScratchPerWarp, "staging row must fit the warp's scratch tile");
 
 struct SplitOut {          // ring of split-precision power-spectrum rows (kSpecPad bf16 each), consumed by mel_gemm.cu
@@ -244,6 +244,7 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
     if (layout == MST_LAYOUT_BIN_MAJOR) {
       // transposed store: clip block is [n_out][T]; the tile's 8 consecutive frames give one 32-byte segment per bin row
       __syncthreads();
+      if (kWarpsPerCta != 8) __trap();
       const int nvalid = min(kWarpsPerCta, cd.frames - t0);
       float* blk = out + cd.frame_offset * n_out;
       const bool vec4 = (cd.frames & 3) == 0 && ((cd.frame_offset * n_out) & 3) == 0 && nvalid == kWarpsPerCta &&
