@@ -72,6 +72,13 @@ int mst_batch_create(int n_clips, const int64_t* h_clip_offsets, const int64_t* 
  * back to back in the output waveform buffer. */
 int mst_batch_create_from_frames(int n_clips, const int64_t* h_frames_per_clip, int n_fft, int hop,
                                  int pad_mode, mst_batch_t** out);
+/* The same with librosa's win_length (<= n_fft): the periodic Hann window of that length, centre-padded to n_fft, is the
+ * analysis window of librosa.stft(..., win_length=) and the analysis + synthesis window (and window-sum-square envelope)
+ * of librosa.griffinlim(..., win_length=) [model/inference.py:110 passes win_length=n_fft]. */
+int mst_batch_create_ex(int n_clips, const int64_t* h_clip_offsets, const int64_t* h_clip_lengths, int n_fft, int hop,
+                        int win_length, int pad_mode, mst_batch_t** out);
+int mst_batch_create_from_frames_ex(int n_clips, const int64_t* h_frames_per_clip, int n_fft, int hop, int win_length,
+                                    int pad_mode, mst_batch_t** out);
 void mst_batch_destroy(mst_batch_t* b);
 int mst_batch_n_clips(const mst_batch_t* b);
 int64_t mst_batch_total_frames(const mst_batch_t* b);

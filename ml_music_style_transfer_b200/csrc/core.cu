@@ -120,9 +120,35 @@ static int batch_finish(mst_batch* b) {
   return MST_OK;
 }
 
-static int batch_check(int n_clips, int n_fft, int hop, int pad_mode) {
+// librosa: get_window('hann', win_length, fftbins=True) centre-padded to n_fft (util.pad_center), in double
+static std::vector<double> padded_hann(int win_length) {
+  std::vector<double> w((size_t)kNfft, 0.0);
+  const double two_pi = 6.283185307179586476925286766559;
+  const int lpad = (kNfft - win_length) / 2;
+  for (int n = 0; n < win_length; ++n) w[(size_t)lpad + n] = 0.5 - 0.5 * cos(two_pi * (double)n / (double)win_length);
+  return w;
+}
+
+// Non-default window length: upload the padded analysis / synthesis windows of this batch.
+static int batch_upload_window(mst_batch* b) {
+  if (b->win_length == kNfft) return MST_OK;  // kernels use the per-device default tables
+  const std::vector<double> w = padded_hann(b->win_length);
+  std::vector<float> wf((size_t)kNfft), ws((size_t)kNfft);
+  for (int n = 0; n < kNfft; ++n) {
+    wf[n] = (float)w[n];
+    ws[n] = wf[n] * (1.0f / 1024.0f);
+  }
+  MST_CUDA_OK(cudaMalloc(&b->d_window, sizeof(float) * kNfft));
+  MST_CUDA_OK(cudaMalloc(&b->d_wsyn, sizeof(float) * kNfft));
+  MST_CUDA_OK(cudaMemcpy(b->d_window, wf.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+  MST_CUDA_OK(cudaMemcpy(b->d_wsyn, ws.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+  return MST_OK;
+}
+
+static int batch_check(int n_clips, int n_fft, int hop, int win_length, int pad_mode) {
   if (n_clips <= 0) return fail(MST_ERR_INVALID, "n_clips must be positive (got %d)", n_clips);
   if (n_fft != kNfft) return fail(MST_ERR_UNSUPPORTED, "n_fft=%d unsupported: this build implements n_fft=2048 only", n_fft);
+  if (win_length < 1 || win_length > n_fft) return fail(MST_ERR_INVALID, "win_length=%d must be in [1, n_fft]", win_length);
   if (hop <= 0 || hop > n_fft) return fail(MST_ERR_INVALID, "hop=%d must be in [1, n_fft]", hop);
   if (pad_mode != MST_PAD_REFLECT && pad_mode != MST_PAD_CONSTANT) return fail(MST_ERR_INVALID, "bad pad_mode %d", pad_mode);
   return MST_OK;
@@ -130,9 +156,14 @@ static int batch_check(int n_clips, int n_fft, int hop, int pad_mode) {
 
 int mst_batch_create(int n_clips, const int64_t* h_clip_offsets, const int64_t* h_clip_lengths, int n_fft, int hop,
                      int pad_mode, mst_batch_t** out) {
+  return mst_batch_create_ex(n_clips, h_clip_offsets, h_clip_lengths, n_fft, hop, n_fft, pad_mode, out);
+}
+
+int mst_batch_create_ex(int n_clips, const int64_t* h_clip_offsets, const int64_t* h_clip_lengths, int n_fft, int hop,
+                        int win_length, int pad_mode, mst_batch_t** out) {
   if (!out || !h_clip_offsets || !h_clip_lengths) return fail(MST_ERR_INVALID, "null argument");
   *out = nullptr;
-  int rc = batch_check(n_clips, n_fft, hop, pad_mode);
+  int rc = batch_check(n_clips, n_fft, hop, win_length, pad_mode);
   if (rc) return rc;
   for (int c = 0; c < n_clips; ++c) {
     if (h_clip_offsets[c] < 0) return fail(MST_ERR_INVALID, "clip %d: negative offset", c);
@@ -143,13 +174,14 @@ int mst_batch_create(int n_clips, const int64_t* h_clip_offsets, const int64_t* 
     if (h_clip_lengths[c] <= 0) return fail(MST_ERR_INVALID, "clip %d: empty clip", c);
   }
   mst_batch* b = new mst_batch();
-  b->n_clips = n_clips; b->n_fft = n_fft; b->hop = hop; b->pad_mode = pad_mode;
+  b->n_clips = n_clips; b->n_fft = n_fft; b->hop = hop; b->pad_mode = pad_mode; b->win_length = win_length;
   b->h_clips = new ClipDesc[n_clips];
   for (int c = 0; c < n_clips; ++c) {
     b->h_clips[c].sample_offset = h_clip_offsets[c];
     b->h_clips[c].length = h_clip_lengths[c];
   }
   rc = batch_finish(b);
+  if (!rc) rc = batch_upload_window(b);
   if (rc) { mst_batch_destroy(b); return rc; }
   *out = b;
   return MST_OK;
@@ -157,12 +189,18 @@ int mst_batch_create(int n_clips, const int64_t* h_clip_offsets, const int64_t* 
 
 int mst_batch_create_from_frames(int n_clips, const int64_t* h_frames, int n_fft, int hop, int pad_mode,
                                  mst_batch_t** out) {
+  return mst_batch_create_from_frames_ex(n_clips, h_frames, n_fft, hop, n_fft, pad_mode, out);
+}
+
+int mst_batch_create_from_frames_ex(int n_clips, const int64_t* h_frames, int n_fft, int hop, int win_length, int pad_mode,
+                                    mst_batch_t** out) {
   if (!out || !h_frames) return fail(MST_ERR_INVALID, "null argument");
   *out = nullptr;
-  int rc = batch_check(n_clips, n_fft, hop, pad_mode);
+  int rc = batch_check(n_clips, n_fft, hop, win_length, pad_mode);
   if (rc) return rc;
   mst_batch* b = new mst_batch();
   b->n_clips = n_clips; b->n_fft = n_fft; b->hop = hop; b->pad_mode = pad_mode; b->from_frames = true;
+  b->win_length = win_length;
   b->h_clips = new ClipDesc[n_clips];
   int64_t off = 0;
   for (int c = 0; c < n_clips; ++c) {
@@ -177,16 +215,14 @@ int mst_batch_create_from_frames(int n_clips, const int64_t* h_frames, int n_fft
     off += len;
   }
   rc = batch_finish(b);
+  if (!rc) rc = batch_upload_window(b);
   if (rc) { mst_batch_destroy(b); return rc; }
   // Griffin-Lim needs 1 / window-sum-square per accumulator position (librosa.istft's normalisation,
   // accumulated in float32 frame by frame like librosa's window_sumsquare).  Clips with equal T share one envelope.
   {
+    const std::vector<double> wd = padded_hann(win_length);
     std::vector<double> wsq(kNfft);
-    const double two_pi = 6.283185307179586476925286766559;
-    for (int n = 0; n < kNfft; ++n) {
-      const double w = 0.5 - 0.5 * cos(two_pi * (double)n / (double)kNfft);
-      wsq[n] = w * w;
-    }
+    for (int n = 0; n < kNfft; ++n) wsq[n] = wd[n] * wd[n];
     std::vector<int64_t> wss_off((size_t)n_clips);
     std::vector<float> env;
     std::vector<std::pair<int32_t, int64_t>> seen;  // (T, offset)
@@ -224,7 +260,7 @@ int mst_batch_create_from_frames(int n_clips, const int64_t* h_frames, int n_fft
       const float tiny = 1.17549435e-38f;
       for (int j = 0; j < kNfft; ++j) {
         const float e = x[(size_t)q * hop + j];
-        const float w = (float)(0.5 - 0.5 * cos(two_pi * (double)j / (double)kNfft));
+        const float w = (float)wd[j];
         wq[j] = w * (e > tiny ? 1.0f / e : 1.0f);
       }
     }
@@ -248,6 +284,8 @@ void mst_batch_destroy(mst_batch_t* b) {
   if (b->d_tile_clip) cudaFree(b->d_tile_clip);
   if (b->d_inv_wss) cudaFree(b->d_inv_wss);
   if (b->d_wq) cudaFree(b->d_wq);
+  if (b->d_window) cudaFree(b->d_window);
+  if (b->d_wsyn) cudaFree(b->d_wsyn);
   if (b->d_wss_offset) cudaFree(b->d_wss_offset);
   delete[] b->h_clips;
   delete b;

@@ -518,6 +518,7 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
   Tables tabs;
   int rc = get_tables(&tabs);
   if (rc) return rc;
+  if (b->d_window) { tabs.window = b->d_window; tabs.wsyn = b->d_wsyn; }  // win_length < n_fft
 
   const size_t spec = (size_t)b->total_frames * kBins;
   char* ws = reinterpret_cast<char*>(d_workspace);

@@ -57,6 +57,9 @@ struct ClipDesc {        // one per clip, device resident
 struct mst_batch {
   int n_clips = 0;
   int n_fft = 0, hop = 0, pad_mode = 0;
+  int win_length = 0;                // <= n_fft; the periodic Hann window of this length is centre-padded to n_fft (librosa)
+  float* d_window = nullptr;         // [n_fft] padded analysis window, NULL = the default table (win_length == n_fft)
+  float* d_wsyn = nullptr;           // [n_fft] padded window / (n_fft / 2): synthesis window with the inverse-FFT scale
   int64_t total_frames = 0, total_samples = 0, total_acc = 0;
   int64_t audio_extent = 0;          // max over clips of sample_offset + length: elements the audio buffer must hold
   int total_tiles = 0;

@@ -274,6 +274,7 @@ static int launch_stft(const float* d_audio, const mst_batch* b, int layout, voi
   Tables tabs;
   int rc = get_tables(&tabs);
   if (rc) return rc;
+  if (b->d_window) tabs.window = b->d_window;  // win_length < n_fft: this batch's centre-padded window
   const size_t smem = kStftSmemBytes;
   static std::atomic<bool> attr_set[64];  // one flag per device and per MODE instantiation
   int dev = 0;

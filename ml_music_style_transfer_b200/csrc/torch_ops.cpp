@@ -36,22 +36,23 @@ void want_cpu_i64(const at::Tensor& t, const char* name) {
 
 // ---- handles (host side) -------------------------------------------------------------------
 int64_t batch_create(const at::Tensor& offsets, const at::Tensor& lengths, int64_t n_fft, int64_t hop, int64_t pad_mode,
-                     int64_t device) {
+                     int64_t device, int64_t win_length) {
   want_cpu_i64(offsets, "clip_offsets");
   want_cpu_i64(lengths, "clip_lengths");
   TORCH_CHECK(offsets.numel() == lengths.numel(), "offsets / lengths size mismatch");
   c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
   mst_batch_t* b = nullptr;
-  check(mst_batch_create((int)offsets.numel(), offsets.data_ptr<int64_t>(), lengths.data_ptr<int64_t>(), (int)n_fft,
-                         (int)hop, (int)pad_mode, &b), "mst_batch_create");
+  check(mst_batch_create_ex((int)offsets.numel(), offsets.data_ptr<int64_t>(), lengths.data_ptr<int64_t>(), (int)n_fft,
+                            (int)hop, (int)win_length, (int)pad_mode, &b), "mst_batch_create");
   return reinterpret_cast<int64_t>(b);
 }
-int64_t batch_create_from_frames(const at::Tensor& frames, int64_t n_fft, int64_t hop, int64_t pad_mode, int64_t device) {
+int64_t batch_create_from_frames(const at::Tensor& frames, int64_t n_fft, int64_t hop, int64_t pad_mode, int64_t device,
+                                 int64_t win_length) {
   want_cpu_i64(frames, "frames_per_clip");
   c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
   mst_batch_t* b = nullptr;
-  check(mst_batch_create_from_frames((int)frames.numel(), frames.data_ptr<int64_t>(), (int)n_fft, (int)hop,
-                                     (int)pad_mode, &b), "mst_batch_create_from_frames");
+  check(mst_batch_create_from_frames_ex((int)frames.numel(), frames.data_ptr<int64_t>(), (int)n_fft, (int)hop,
+                                        (int)win_length, (int)pad_mode, &b), "mst_batch_create_from_frames");
   return reinterpret_cast<int64_t>(b);
 }
 void batch_destroy(int64_t h) { if (h) mst_batch_destroy(reinterpret_cast<mst_batch_t*>(h)); }
@@ -319,8 +320,8 @@ at::Tensor mono_mix(const at::Tensor& frames) {
 
 TORCH_LIBRARY(mst_b200, m) {
   // host-side handles / helpers (no dispatch key: they take no device tensors)
-  m.def("batch_create(Tensor clip_offsets, Tensor clip_lengths, int n_fft, int hop, int pad_mode, int device) -> int", &batch_create);
-  m.def("batch_create_from_frames(Tensor frames_per_clip, int n_fft, int hop, int pad_mode, int device) -> int", &batch_create_from_frames);
+  m.def("batch_create(Tensor clip_offsets, Tensor clip_lengths, int n_fft, int hop, int pad_mode, int device, int win_length) -> int", &batch_create);
+  m.def("batch_create_from_frames(Tensor frames_per_clip, int n_fft, int hop, int pad_mode, int device, int win_length) -> int", &batch_create_from_frames);
   m.def("batch_destroy(int handle) -> ()", &batch_destroy);
   m.def("batch_total_frames(int handle) -> int", &batch_total_frames);
   m.def("batch_total_samples(int handle) -> int", &batch_total_samples);

@@ -28,12 +28,17 @@ def _pad_code(pad_mode):
 
 
 def _check_window(window, win_length, n_fft):
+    """-> win_length to use.  window='hann' (any win_length <= n_fft, centre-padded like librosa) and n_fft = 2048."""
     if window != "hann":
         raise NotImplementedError("only window='hann' is implemented (the reference uses no other)")
     if n_fft != N_FFT:
         raise NotImplementedError("n_fft=2048 is the only size the reference uses and the only one built")
-    if win_length not in (None, n_fft):
-        raise NotImplementedError("win_length must equal n_fft")
+    if win_length is None:
+        return n_fft
+    win_length = int(win_length)
+    if not 1 <= win_length <= n_fft:
+        raise ValueError(f"win_length={win_length} must be in [1, n_fft]")
+    return win_length
 
 
 class ClipBatch:
@@ -46,12 +51,13 @@ class ClipBatch:
         self.total_samples = int(o.batch_total_samples(handle))
 
     @classmethod
-    def from_clips(cls, offsets, lengths, hop, pad_mode="reflect", device=None, n_fft=N_FFT):
+    def from_clips(cls, offsets, lengths, hop, pad_mode="reflect", device=None, n_fft=N_FFT, win_length=None):
         device = _lib.require_cuda(device)
         offsets = torch.as_tensor(np.asarray(offsets, dtype=np.int64))
         lengths = torch.as_tensor(np.asarray(lengths, dtype=np.int64))
         try:
-            h = _lib.ops().batch_create(offsets, lengths, n_fft, int(hop), _pad_code(pad_mode), device.index)
+            h = _lib.ops().batch_create(offsets, lengths, n_fft, int(hop), _pad_code(pad_mode), device.index,
+                                        n_fft if win_length is None else int(win_length))
         except RuntimeError as e:
             if "too short" in str(e) or "empty clip" in str(e):
                 # np.pad(mode='reflect') / librosa raise for inputs shorter than the padding: keep the exception type
@@ -60,17 +66,19 @@ class ClipBatch:
         return cls(h, int(offsets.numel()), int(hop), device)
 
     @classmethod
-    def uniform(cls, n_clips, clip_length, hop, clip_stride=None, pad_mode="reflect", device=None):
+    def uniform(cls, n_clips, clip_length, hop, clip_stride=None, pad_mode="reflect", device=None, win_length=None):
         stride = clip_length if clip_stride is None else clip_stride
         offsets = np.arange(n_clips, dtype=np.int64) * stride
-        return cls.from_clips(offsets, np.full(n_clips, clip_length, dtype=np.int64), hop, pad_mode, device)
+        return cls.from_clips(offsets, np.full(n_clips, clip_length, dtype=np.int64), hop, pad_mode, device,
+                              win_length=win_length)
 
     @classmethod
-    def from_frames(cls, frames_per_clip, hop, pad_mode="reflect", device=None, n_fft=N_FFT):
+    def from_frames(cls, frames_per_clip, hop, pad_mode="reflect", device=None, n_fft=N_FFT, win_length=None):
         device = _lib.require_cuda(device)
         frames = torch.as_tensor(np.asarray(frames_per_clip, dtype=np.int64))
         try:
-            h = _lib.ops().batch_create_from_frames(frames, n_fft, int(hop), _pad_code(pad_mode), device.index)
+            h = _lib.ops().batch_create_from_frames(frames, n_fft, int(hop), _pad_code(pad_mode), device.index,
+                                                    n_fft if win_length is None else int(win_length))
         except RuntimeError as e:
             if "too short" in str(e):
                 raise ValueError(str(e)) from None
@@ -179,12 +187,12 @@ def melspectrogram_batch(audio, batch, plan, log1p=False, layout=FRAME_MAJOR):
 
 def stft(y, n_fft=N_FFT, hop_length=None, win_length=None, window="hann", center=True, pad_mode="reflect"):
     """librosa.stft drop-in for one clip: complex64 (1025, T), Fortran-ordered like librosa's result."""
-    _check_window(window, win_length, n_fft)
+    win_length = _check_window(window, win_length, n_fft)
     if not center:
         raise NotImplementedError("center=False is not used by the reference")
-    hop = n_fft // 4 if hop_length is None else int(hop_length)
+    hop = win_length // 4 if hop_length is None else int(hop_length)
     a, was_np = _to_device_audio(y)
-    with ClipBatch.uniform(1, a.numel(), hop, pad_mode=pad_mode, device=a.device) as b:
+    with ClipBatch.uniform(1, a.numel(), hop, pad_mode=pad_mode, device=a.device, win_length=win_length) as b:
         out = stft_batch(a, b, "complex")  # [T][1025] memory; its transpose view == librosa's Fortran-ordered (1025, T)
     return to_numpy(out).T if was_np else out.t()
 
@@ -238,8 +246,8 @@ def griffinlim(S, n_iter=32, hop_length=None, win_length=None, window="hann", mo
     if S.dim() != 2 or S.shape[0] != N_BINS:
         raise ValueError(f"S must be (1025, T); got {tuple(S.shape)}")
     n_fft = 2 * (S.shape[0] - 1)
-    _check_window(window, win_length, n_fft)
-    hop = n_fft // 4 if hop_length is None else int(hop_length)
+    win_length = _check_window(window, win_length, n_fft)
+    hop = win_length // 4 if hop_length is None else int(hop_length)
     T = int(S.shape[1])
     if init_phase is None and init == "random" and isinstance(random_state, (int, np.integer)):
         init_phase = np.random.RandomState(int(random_state)).rand(N_BINS, T)
@@ -253,7 +261,7 @@ def griffinlim(S, n_iter=32, hop_length=None, win_length=None, window="hann", mo
         layout, S_flat = BIN_MAJOR, S.contiguous()
         ph = None if init_phase is None else init_phase.to(torch.float32).contiguous()
     seed = int(np.random.randint(0, 2 ** 31 - 1))
-    with ClipBatch.from_frames([T], hop, pad_mode=pad_mode, device=device) as b:
+    with ClipBatch.from_frames([T], hop, pad_mode=pad_mode, device=device, win_length=win_length) as b:
         y = griffinlim_batch(S_flat.to(torch.float32), b, n_iter, momentum, ph, init, seed, layout)
     return to_numpy(y) if was_np else y
 

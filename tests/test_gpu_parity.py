@@ -628,6 +628,31 @@ def test_other_hops(pkg, hop):
         assert rel_l2(w_got, w_ref.astype(np.float64)) < 5e-4, (hop, n_iter, rel_l2(w_got, w_ref.astype(np.float64)))
 
 
+@pytest.mark.parametrize("win_length,hop", [(1024, 256), (1500, 375), (2047, 512), (400, None)])
+def test_win_length_shorter_than_n_fft(pkg, win_length, hop):
+    """librosa.stft / griffinlim with win_length < n_fft: periodic Hann of that length, centre-padded to 2048 -- analysis
+    window, synthesis window and window-sum-square envelope all follow (the reference passes win_length = n_fft)."""
+    y = clip(37, 24000)
+    ref = ostft.stft(y, 2048, hop, win_length=win_length)
+    got = pkg.features.stft(y, hop_length=hop, win_length=win_length)
+    assert got.shape == ref.shape
+    assert_close(got, ref)
+    h = win_length // 4 if hop is None else hop
+    S = np.abs(ref).astype(np.float32)
+    u = ogl.random_phase(S.shape, 6)
+    for n_iter in (0, 2):
+        w_ref = ogl.griffinlim(S, n_iter, h, win_length=win_length, init_phase=u)
+        w_got = pkg.features.griffinlim(S, n_iter=n_iter, hop_length=hop, win_length=win_length, init_phase=u)
+        assert w_got.shape == w_ref.shape
+        assert rel_l2(w_got, w_ref.astype(np.float64)) < 5e-4, (win_length, n_iter, rel_l2(w_got, w_ref.astype(np.float64)))
+    w_ref = ogl.griffinlim(S, 16, h, win_length=win_length, init_phase=u)
+    w_got = pkg.features.griffinlim(S, n_iter=16, hop_length=hop, win_length=win_length, init_phase=u)
+    sc = lambda w: ogl.spectral_convergence(S, w, h, win_length=win_length)
+    assert abs(sc(w_ref) - sc(w_got)) <= 1e-3, (sc(w_ref), sc(w_got))
+    with pytest.raises(ValueError):
+        pkg.features.stft(y, hop_length=256, win_length=4096)
+
+
 @pytest.mark.parametrize("hop", [128, 256, 512, 1024])
 def test_griffinlim_all_tile_remainders(pkg, gpu, hop):
     """Every frame count from the shortest legal clip up to 3+ tiles in ONE ragged batch: exercises first / last / only
