@@ -387,9 +387,13 @@ def run_ours(args):
         if traffic is None and os.path.exists(tpath):
             with open(tpath) as f:  # ncu: dram__bytes_read.sum + dram__bytes_write.sum of one GL iteration launch
                 tj = json.load(f)
-            traffic = tj["gl_iteration_dram_bytes_per_clip"] * n_clips
-            traffic_src = tj.get("source", "profiles/traffic.json") + ("" if tj.get("clips") == n_clips else
-                                                                          f" -- scaled from {tj.get('clips')} to {n_clips} clips")
+            # captured on 173-frame clips: scale per FRAME when this run's geometry differs (the kernel's traffic is per frame)
+            per_frame = tj["gl_iteration_dram_bytes_per_clip"] / float(tj.get("frames_per_clip", 173))
+            traffic = per_frame * T_FRAMES * n_clips
+            same = tj.get("clips") == n_clips and tj.get("frames_per_clip", 173) == T_FRAMES
+            traffic_src = tj.get("source", "profiles/traffic.json") + (
+                "" if same else f" -- scaled per frame from {tj.get('clips')} x {tj.get('frames_per_clip', 173)} to "
+                                f"{n_clips} x {T_FRAMES} frames")
         line = {
             "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -652,7 +656,7 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling pass (16384 clips in total) at N > 1")
     ap.add_argument("--no-single", action="store_true", help="skip the single 30 s clip latency section")
     ap.add_argument("--e2e-clips", type=int, default=None, help="clips per GPU for the host-buffer end-to-end pass (default: the same as --clips)")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline depth of the end-to-end pass (chunks rotating over MST_E2E_STREAMS streams, default 4)")
+    ap.add_argument("--e2e-chunks", type=int, default=32, help="pipeline depth of the end-to-end pass (chunks rotating over MST_E2E_STREAMS streams, default 4)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -87,6 +87,11 @@ def rasterize(notes, fs, want_velsum=False, pedal_threshold=64):
     pretty_midi >= 0.2.9 (``pedal_threshold``, None = off) is applied before binarising.
     """
     o = _lib.ops()
+    if int(fs) != fs or fs <= 0:
+        # the kernels take an integer rate (the reference's hp.wps = sr // ws is one); a fractional fs would size the rows
+        # on the host with one value and place the columns on the device with another
+        raise ValueError(f"fs={fs!r} must be a positive integer")
+    fs = int(fs)
     h_end = notes.end_times if notes.end_times is not None else getattr(notes, "h_max_end", None)
     if h_end is not None:
         # int(fs * end_time) on the host is the same IEEE double product the device kernel evaluates
