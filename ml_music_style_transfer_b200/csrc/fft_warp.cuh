@@ -83,6 +83,18 @@ __device__ __forceinline__ float2 pk_mul(float2 a, float2 b) { return make_float
 __device__ __forceinline__ float2 pk_bcast(float s) { return make_float2(s, s); }
 __device__ __forceinline__ float2 pk_neg(float2 a) { return make_float2(-a.x, -a.y); }
 
+// Shared-memory table reads in groups (MST_LDS_BATCH per group, issued back to back as volatile loads so that ptxas keeps
+// them together): with 4 warps per scheduler a 29-cycle LDS latency per table entry cannot be hidden by other warps, and
+// ptxas otherwise schedules each load right before its single use (ncu: short_scoreboard 17 % of the stall samples).
+#ifndef MST_LDS_BATCH
+#define MST_LDS_BATCH 4
+#endif
+__device__ __forceinline__ float2 lds64(const float2* p) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
+
 // a * b (complex):  (a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x) = a.x * b + a.y * (-b.y, b.x).  The half-swapped,
 // half-negated pair must be the FIRST operand of the FFMA2: there ptxas folds swap and sign into operand modifiers
 // (-R4.F32x2.LO_HI.NP); as second operand, or in an FMUL2, it is materialised with extra FADD / MOV instructions.
@@ -149,6 +161,25 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
   StageLoop<SIGN, 16, 0, 0>::run(v);
 }
 
+// Between the two FFT-32 passes: multiply by the W_1024^(k1*n2) twiddles and park the column in the transpose tile.
+template <int SIGN>
+__device__ __forceinline__ void twiddle_and_park(float2 (&v)[32], float2* scratch, const float2* tw, int lane) {
+#pragma unroll
+  for (int g = 0; g < 32; g += MST_LDS_BATCH) {
+    float2 w[MST_LDS_BATCH];
+#pragma unroll
+    for (int i = 0; i < MST_LDS_BATCH; ++i)
+      if (g + i != 0) w[i] = MST_LDS_BATCH > 1 ? lds64(tw + (g + i) * 32 + lane) : tw[(g + i) * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < MST_LDS_BATCH; ++i) {
+      const int k1 = g + i;
+      float2 a = v[br5(k1)];
+      if (k1 != 0) a = SIGN > 0 ? cmul_conj(a, w[i]) : cmul(a, w[i]);
+      scratch[k1 * 33 + lane] = a;
+    }
+  }
+}
+
 // 1024-point complex FFT across one warp.  `scratch` is this warp's 32x33 float2 tile,
 // `tw` the shared-memory table exp(-2*pi*i*k1*n2/1024) laid out [k1][n2].
 // fft1024_front leaves the transposed intermediate in v[] and the scratch tile FREE (callers may start asynchronous
@@ -156,15 +187,7 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
 template <int SIGN>
 __device__ __forceinline__ void fft1024_front(float2 (&v)[32], float2* scratch, const float2* tw, int lane) {
   fft32<SIGN>(v);
-#pragma unroll
-  for (int k1 = 0; k1 < 32; ++k1) {
-    float2 a = v[br5(k1)];
-    if (k1 != 0) {
-      const float2 w = tw[k1 * 32 + lane];
-      a = SIGN > 0 ? cmul_conj(a, w) : cmul(a, w);
-    }
-    scratch[k1 * 33 + lane] = a;
-  }
+  twiddle_and_park<SIGN>(v, scratch, tw, lane);
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = scratch[lane * 33 + j];
@@ -186,15 +209,7 @@ __device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* scratch, c
   for (int pass = 0; pass < 2; ++pass) {
     fft32<SIGN>(v);
     if (pass == 0) {
-#pragma unroll
-      for (int k1 = 0; k1 < 32; ++k1) {
-        float2 a = v[br5(k1)];
-        if (k1 != 0) {
-          const float2 w = tw[k1 * 32 + lane];
-          a = SIGN > 0 ? cmul_conj(a, w) : cmul(a, w);
-        }
-        scratch[k1 * 33 + lane] = a;
-      }
+      twiddle_and_park<SIGN>(v, scratch, tw, lane);
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = scratch[lane * 33 + j];
@@ -236,13 +251,20 @@ __device__ __forceinline__ void pair_butterfly(float2 z, float2 p, float2 w, flo
 __device__ __forceinline__ void rfft_split(float2 (&v)[32], float2 (&o)[32], float2* mid, const float2* twp, int lane) {
   const int src = (32 - lane) & 31;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const float2 z = v[br5(r)];
-    float2 p;
-    p.x = __shfl_sync(MST_FULL_MASK, v[br5(31 - r)].x, src);
-    p.y = __shfl_sync(MST_FULL_MASK, v[br5(31 - r)].y, src);
-    if (lane == 0) p = v[br5((32 - r) & 31)];  // lane 0 pairs with itself: bin 32*r <-> bin 32*(32-r); r = 0 -> Z[0]
-    pair_butterfly<false>(z, p, twp[lane + 32 * r], o[r], o[31 - r]);
+  for (int g = 0; g < 16; g += MST_LDS_BATCH) {
+    float2 w[MST_LDS_BATCH];
+#pragma unroll
+    for (int i = 0; i < MST_LDS_BATCH; ++i) w[i] = MST_LDS_BATCH > 1 ? lds64(twp + lane + 32 * (g + i)) : twp[lane + 32 * (g + i)];
+#pragma unroll
+    for (int i = 0; i < MST_LDS_BATCH; ++i) {
+      const int r = g + i;
+      const float2 z = v[br5(r)];
+      float2 p;
+      p.x = __shfl_sync(MST_FULL_MASK, v[br5(31 - r)].x, src);
+      p.y = __shfl_sync(MST_FULL_MASK, v[br5(31 - r)].y, src);
+      if (lane == 0) p = v[br5((32 - r) & 31)];  // lane 0 pairs with itself: bin 32*r <-> bin 32*(32-r); r = 0 -> Z[0]
+      pair_butterfly<false>(z, p, w[i], o[r], o[31 - r]);
+    }
   }
   {
     const float2 z = v[br5(16)];  // lane 0: Z[512], its own partner
@@ -265,10 +287,17 @@ __device__ __forceinline__ void irfft2048_warp(float2 (&y)[32], float2 mid, floa
   const int src = (32 - lane) & 31;
   float2 t[16];  // merged values for bins 1024-k, to be handed to the mirrored lane
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    float2 a = y[r], b = y[31 - r];
-    if (r == 0 && lane == 0) { a.y = 0.0f; b.y = 0.0f; }  // DC / Nyquist
-    pair_butterfly<true>(a, b, twp[lane + 32 * r], v[r], t[r]);
+  for (int g = 0; g < 16; g += MST_LDS_BATCH) {
+    float2 w[MST_LDS_BATCH];
+#pragma unroll
+    for (int i = 0; i < MST_LDS_BATCH; ++i) w[i] = MST_LDS_BATCH > 1 ? lds64(twp + lane + 32 * (g + i)) : twp[lane + 32 * (g + i)];
+#pragma unroll
+    for (int i = 0; i < MST_LDS_BATCH; ++i) {
+      const int r = g + i;
+      float2 a = y[r], b = y[31 - r];
+      if (r == 0 && lane == 0) { a.y = 0.0f; b.y = 0.0f; }  // DC / Nyquist
+      pair_butterfly<true>(a, b, w[i], v[r], t[r]);
+    }
   }
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
