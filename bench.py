@@ -196,8 +196,26 @@ def run_ours(args):
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
+    # The timed step runs the three stages through the package's DevicePipeline: the batch is cut into chunks that rotate
+    # over 4 CUDA streams, so the write-bound roll writer and the FP32-bound log-mel of one chunk run under the
+    # latency-bound Griffin-Lim of another (same kernels, same work, every launch counted).  --serial times the three
+    # stages back to back on one stream instead; `stages` below are always measured that way, each stage alone.
+    dpipe = None
+    if not args.serial:
+        from ml_music_style_transfer_b200.pipeline import DevicePipeline
+        dpipe = DevicePipeline(n_clips, CLIP_LEN, notes_h, sr=SR, hop=HOP, n_mels=N_MELS, roll_fs=ROLL_FS, pitch_lo=PITCH_LO,
+                               n_keys=N_KEYS, gl_iters=GL_ITERS, n_chunks=args.step_chunks, device=device, plan=plan)
+
+    def step():
+        if dpipe is not None:
+            dpipe.run(audio, S)
+        else:
+            stage_a(); stage_b(); stage_c()
+
     # warm-up (W >= 3 steps)
     for _ in range(max(3, args.warmup)):
+        step()
+    for _ in range(2):
         stage_a(); stage_b(); stage_c()
     barrier()
 
@@ -211,13 +229,16 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        ta += timed(stage_a, 1); tb += timed(stage_b, 1); tc += timed(stage_c, 1)
+        step()
     ev1.record()
     barrier()
     total_ms = ev0.elapsed_time(ev1)
     wall_s = time.perf_counter() - t_wall0
     launches = pkg._lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    # per-stage figures: each stage alone on one stream (not part of `value`)
+    for _ in range(max(3, min(args.steps, 5))):
+        ta += timed(stage_a, 1); tb += timed(stage_b, 1); tc += timed(stage_c, 1)
 
     # reference point for the write-only stage: what the driver's own device memset achieves on this GPU (measured live;
     # tools/ubench.cu has the full study: memset 7.4 TB/s, one-shot st.global.v4 grid 7.6, grid-stride 6.2-6.9, bulk
@@ -303,6 +324,11 @@ def run_ours(args):
                 PR.upsample_pair(roll, onoff, row_off[q0:q1 + 1], CLIP_LEN, ROLL_FS, SR, PITCH_LO, N_KEYS, torch.int8)
             return F.griffinlim_batch(S[:m * T_FRAMES * K], gl_s, n_iter=GL_ITERS, momentum=0.99, init="random", seed=7,
                                       layout=F.FRAME_MAJOR)
+        if not args.serial:
+            sp = DevicePipeline(m, CLIP_LEN, tuple(a[:offs[m]] for a in notes_h[:4]) + (offs[:m + 1],), sr=SR, hop=HOP,
+                                n_mels=N_MELS, roll_fs=ROLL_FS, pitch_lo=PITCH_LO, n_keys=N_KEYS, gl_iters=GL_ITERS,
+                                n_chunks=max(1, args.step_chunks // world), device=device, plan=plan)
+            step_s = lambda: sp.run(audio[:m * CLIP_LEN], S[:m * T_FRAMES * K])   # noqa: E731
         for _ in range(3):
             step_s()
         barrier()
@@ -405,7 +431,11 @@ def run_ours(args):
                        "clips_per_gpu": n_clips,
                        "l2_policy": f"inputs larger than L2 ({n_clips * CLIP_LEN * 4 / 1e9:.1f} GB audio, "
                                     f"{n_clips * T_FRAMES * K * 4 / 1e9:.1f} GB spectrogram per GPU)",
-                       "parallelism": f"clips sharded over {world} GPU(s), no data-path collective"},
+                       "parallelism": f"clips sharded over {world} GPU(s), no data-path collective",
+                       "step_schedule": ("serial: stages back to back on one stream" if dpipe is None else
+                                         f"pipeline.DevicePipeline: {len(dpipe.chunks)} chunks over {dpipe.n_streams} streams "
+                                         "(stages of different chunks overlap; `stages` are each stage alone)")},
+            "stages_serial_ms": ma + mb + mc,
             "stages": stages,
             "roofline": {"bound": "hbm", "kernel": "gl_kernel<false> (one Griffin-Lim iteration)", "achieved": achieved,
                          "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -659,6 +689,9 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=32, help="pipeline depth of the end-to-end pass (chunks rotating over MST_E2E_STREAMS streams, default 4)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="time the three stages back to back on one stream instead of the "
+                                                        "chunk-pipelined DevicePipeline schedule")
+    ap.add_argument("--step-chunks", type=int, default=32, help="chunks of the pipelined step (rotating over 4 streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per GL-iteration launch (from profiles/)")
     args = ap.parse_args()

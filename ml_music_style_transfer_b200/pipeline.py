@@ -134,3 +134,81 @@ class HostPipeline:
         if self.planes_to_host:
             d2h += 2 * self.n * self.n_keys * self.clip_len
         return int(h2d), int(d2h)
+
+
+class DevicePipeline:
+    """The same chunked, multi-stream schedule for inputs that already live in HBM and results that stay there.
+
+    The three stages have different bottlenecks (log-mel: FP32 pipe; audio-rate rolls: HBM writes; Griffin-Lim: shared
+    memory / latency), so running chunk k's stages while chunk k-1's Griffin-Lim is still in flight -- chunks rotate over
+    `n_streams` CUDA streams -- fills units a single stream leaves idle.  ``run`` returns after joining the streams on
+    the caller's stream (no host synchronisation).  With ``collect=True`` the log-mel, waveforms and frame-rate rolls of
+    every chunk are gathered into full-size device tensors (``self.mel / wave / roll / onoff``); the audio-rate planes
+    (15.5 MB per 4 s clip) are handed to ``plane_consumer(chunk_start, chunk_stop, up_roll, up_onoff)`` chunk by chunk.
+    """
+
+    def __init__(self, n_clips, clip_len, notes, sr=22050, hop=512, n_mels=128, roll_fs=250, pitch_lo=21, n_keys=88,
+                 gl_iters=32, n_chunks=32, n_streams=4, collect=False, plane_consumer=None, device=None, plan=None):
+        self.device = _lib.require_cuda(device)
+        self.n, self.clip_len, self.sr, self.hop = int(n_clips), int(clip_len), int(sr), int(hop)
+        self.n_mels, self.roll_fs, self.pitch_lo, self.n_keys, self.gl_iters = n_mels, roll_fs, pitch_lo, n_keys, gl_iters
+        self.frames = 1 + self.clip_len // self.hop
+        self.wave_len = self.hop * (self.frames - 1)
+        self.seconds = self.clip_len / float(self.sr)
+        self.rows_per_clip = int(self.roll_fs * self.seconds)
+        self.plan = plan if plan is not None else F.MelPlan.get(sr, F.N_FFT, n_mels, device=self.device)
+        self.n_streams = max(1, int(n_streams))
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)]
+        n_chunks = max(1, min(int(n_chunks), self.n // 256)) if self.n >= 512 else 1
+        bounds = [(self.n * i) // n_chunks for i in range(n_chunks + 1)]
+        self.plane_sub = max(1, min(self.n, int(256 * 4.0 / max(self.seconds, 1e-3))))
+        pitch, vel, start, end, off = notes
+        off = np.asarray(off, dtype=np.int64)
+        self.chunks = []
+        for ci in range(n_chunks):
+            a0, a1 = bounds[ci], bounds[ci + 1]
+            n0, n1 = int(off[a0]), int(off[a1])
+            nb = PR.NoteBatch(pitch[n0:n1], vel[n0:n1], start[n0:n1], end[n0:n1], off[a0:a1 + 1] - off[a0],
+                              device=self.device, end_times=[self.seconds] * (a1 - a0))
+            self.chunks.append(dict(a0=a0, a1=a1, m=a1 - a0, notes=nb,
+                                    batch=F.ClipBatch.uniform(a1 - a0, self.clip_len, self.hop, device=self.device),
+                                    gl_batch=F.ClipBatch.from_frames([self.frames] * (a1 - a0), self.hop, device=self.device)))
+        self.collect, self.plane_consumer = bool(collect), plane_consumer
+        if self.collect:
+            dev = self.device
+            self.mel = torch.empty(self.n * n_mels * self.frames, dtype=torch.float32, device=dev)
+            self.wave = torch.empty(self.n * self.wave_len, dtype=torch.float32, device=dev)
+            self.roll = torch.empty((self.n * self.rows_per_clip, 128), dtype=torch.uint8, device=dev)
+            self.onoff = torch.empty((self.n * self.rows_per_clip, 128), dtype=torch.int8, device=dev)
+
+    def run(self, audio, S, seed=7):
+        """audio: CUDA float32 [n * clip_len]; S: CUDA float32 frame-major magnitudes [n * frames * 1025]."""
+        K = F.N_BINS
+        main = torch.cuda.current_stream(self.device)
+        for s_ in self.streams:
+            s_.wait_stream(main)
+        for ci, ch in enumerate(self.chunks):
+            a0, a1, m = ch["a0"], ch["a1"], ch["m"]
+            with torch.cuda.stream(self.streams[ci % self.n_streams]):
+                mel = F.melspectrogram_batch(audio[a0 * self.clip_len:a1 * self.clip_len], ch["batch"], self.plan, log1p=True,
+                                             layout=F.BIN_MAJOR)
+                roll, onoff, row_off, _ = PR.rasterize(ch["notes"], self.roll_fs)
+                for s in range(0, m, self.plane_sub):
+                    e = min(m, s + self.plane_sub)
+                    ua, ub, _ = PR.upsample_pair(roll, onoff, row_off[s:e + 1], self.clip_len, self.roll_fs, self.sr,
+                                                 self.pitch_lo, self.n_keys, torch.int8)
+                    if self.plane_consumer is not None:
+                        self.plane_consumer(a0 + s, a0 + e, ua, ub)
+                y = F.griffinlim_batch(S[a0 * self.frames * K:a1 * self.frames * K], ch["gl_batch"], n_iter=self.gl_iters,
+                                       momentum=0.99, init="random", seed=seed, layout=F.FRAME_MAJOR)
+                if self.collect:
+                    self.mel[a0 * self.n_mels * self.frames:a1 * self.n_mels * self.frames].copy_(mel)
+                    self.wave[a0 * self.wave_len:a1 * self.wave_len].copy_(y)
+                    r0 = a0 * self.rows_per_clip
+                    self.roll[r0:r0 + m * self.rows_per_clip].copy_(roll)
+                    self.onoff[r0:r0 + m * self.rows_per_clip].copy_(onoff)
+                # the chunk's temporaries were allocated on this side stream: the caching allocator may hand them to the
+                # next chunk of the SAME stream only, which is ordered after this one
+        for s_ in self.streams:
+            main.wait_stream(s_)
+        return self
