@@ -280,6 +280,16 @@ __global__ void __launch_bounds__(256, 4) upsample_kernel(const int8_t* __restri
       const int64_t head = mis < N ? mis : N;
       const int64_t nvec = (N - head) / EPV;
       const int64_t n_chunks = (nvec + 32 * kUpVec - 1) / (32 * kUpVec);
+#ifndef MST_UP_ROWPTR
+#define MST_UP_ROWPTR 1
+#endif
+      // vector-aligned start of this key row in both outputs, and the row's first roll byte in both planes: computed once
+      // per row and kept opaque (otherwise ptxas re-derives them from the kernel parameters in front of every store)
+      OUT* vrow[2] = {out0 + row_base + head, (NP > 1 ? out1 : out0) + row_base + head};
+      const int8_t* srow[2] = {plane0 + src_off, (NP > 1 ? plane1 : plane0) + src_off};
+#if MST_UP_ROWPTR
+      asm volatile("" : "+l"(vrow[0]), "+l"(vrow[1]), "+l"(srow[0]), "+l"(srow[1]));
+#endif
       for (int64_t chunk = (int64_t)blockIdx.x * warps_per_cta + warp; chunk < (n_chunks > 0 ? n_chunks : 1);
            chunk += (int64_t)gridDim.x * warps_per_cta) {
         if (chunk == 0) {
@@ -310,7 +320,7 @@ __global__ void __launch_bounds__(256, 4) upsample_kernel(const int8_t* __restri
           int b0 = 0, b1 = 0;   // staged columns c0 + lane and c0 + 32 + lane: byte q = plane q
 #pragma unroll
           for (int q = 0; q < NP; ++q) {
-            const int8_t* src = planes[q] + src_off;
+            const int8_t* src = srow[q];
             const int x0 = c0 + lane < T ? (int)(uint8_t)src[(c0 + lane) * 128] : 0;
             const int x1 = c0 + 32 + lane < T ? (int)(uint8_t)src[(c0 + 32 + lane) * 128] : 0;
             b0 |= x0 << (8 * q);
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(256, 4) upsample_kernel(const int8_t* __restri
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
               const uint4 val = splat_vector<OUT>((int8_t)((first >> (8 * q)) & 0xff));
-              OUT* dst = outs[q] + row_base + head;
+              OUT* dst = vrow[q];
 #pragma unroll
               for (int u = 0; u < kUpVec; ++u)
                 if (v + 32 * u < nvec) *reinterpret_cast<uint4*>(dst + (v + 32 * u) * EPV) = val;
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(256, 4) upsample_kernel(const int8_t* __restri
             if (v < nvec) {
 #pragma unroll
               for (int q = 0; q < NP; ++q)
-                *reinterpret_cast<uint4*>(outs[q] + row_base + head + v * EPV) =
+                *reinterpret_cast<uint4*>(vrow[q] + v * EPV) =
                     make_vector<OUT>((int8_t)((cur2 >> (8 * q)) & 0xff), (int8_t)((nxt2 >> (8 * q)) & 0xff), e_cross);
             }
             v += 32;
@@ -357,8 +367,8 @@ __global__ void __launch_bounds__(256, 4) upsample_kernel(const int8_t* __restri
           if (v >= nvec) break;
 #pragma unroll
           for (int q = 0; q < NP; ++q) {
-            const int8_t* src = planes[q] + src_off;
-            OUT* dst = outs[q] + row_base + head + v * EPV;
+            const int8_t* src = srow[q];
+            OUT* dst = vrow[q] + v * EPV;
             const int8_t cur = col < T ? src[col * 128] : (int8_t)0;
             if (simple) {
               const int8_t nxt = col + 1 < T ? src[(col + 1) * 128] : (int8_t)0;
