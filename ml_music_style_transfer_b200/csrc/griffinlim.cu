@@ -359,7 +359,7 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
 }
 
 template <bool INIT, bool FIRST>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gl_kernel(GlParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) gl_kernel(GlParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const GlSmem m = gl_smem_setup(smem_raw, P);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -400,7 +400,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm)
 gl_persistent_kernel(GlParams P, int n_iter, float* acc0, float* acc1, float* acc2, unsigned int* barrier, float* y_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const GlSmem m = gl_smem_setup(smem_raw, P);
@@ -557,7 +557,7 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
     MST_CUDA_OK(cudaFuncSetAttribute(gl_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[dev].store(true, std::memory_order_release);
   }
-  const int grid = std::min(b->total_tiles, 2 * sms);
+  const int grid = std::min(b->total_tiles, kCtasPerSm * sms);
 
   MST_CUDA_OK(cudaMemsetAsync(acc[0], 0, acc_bytes, s));
   MST_CUDA_OK(cudaMemsetAsync(acc[1], 0, acc_bytes, s));
@@ -581,13 +581,13 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
       if (coop && cudaFuncSetAttribute(gl_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gl_persistent_kernel, kWarpsPerCta * 32, smem) == cudaSuccess &&
-          per_sm >= 2)
+          per_sm >= kCtasPerSm)
         coop_ok[dev].store(1, std::memory_order_release);
       else
         coop_ok[dev].store(-1, std::memory_order_release);
       cudaGetLastError();
     }
-    if (coop_ok[dev].load(std::memory_order_acquire) == 1 && b->total_tiles <= 2 * sms) {
+    if (coop_ok[dev].load(std::memory_order_acquire) == 1 && b->total_tiles <= kCtasPerSm * sms) {
       unsigned int* barrier = reinterpret_cast<unsigned int*>(ws);  // the 256 spare bytes at the end of the workspace
       MST_CUDA_OK(cudaMemsetAsync(barrier, 0, 256, s));
       MST_CUDA_OK(cudaMemsetAsync(tprev, 0, (size_t)b->total_frames * kSpecStride * sizeof(float2), s));

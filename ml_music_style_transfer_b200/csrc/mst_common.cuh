@@ -18,6 +18,7 @@ constexpr int kHalf = kNfft / 2;      // complex FFT length (even/odd packing) a
 #define MST_WARPS_PER_CTA 8
 #endif
 constexpr int kWarpsPerCta = MST_WARPS_PER_CTA;
+constexpr int kCtasPerSm = kWarpsPerCta <= 10 ? 2 : 1;  // resident CTAs per SM the FFT kernels are sized for
 constexpr int kScratchPerWarp = 32 * 33;  // float2 elements: padded 32x32 transpose tile == one 2048-sample frame slot
 
 // ---- error plumbing -----------------------------------------------------------------------

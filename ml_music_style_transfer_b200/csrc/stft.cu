@@ -84,10 +84,19 @@ __device__ __forceinline__ float2 epilogue_pair(float2 a, float2 b) {
   return p;
 }
 
-constexpr size_t kStftSmemBytes = 8192 + sizeof(float2) * kTwpCount + 8192 + sizeof(float2) * kScratchPerWarp * kWarpsPerCta;
+// GROUPS = tiles (groups of 8 warps) one CTA works on at a time.  The frame-major / complex / split / convergence paths
+// have no cross-warp communication, so they run as ONE CTA of 16 warps per SM (GROUPS = 2): the tables are staged once
+// per SM instead of twice, 152 KB instead of 176 KB of shared memory leave the L1 twice the room for the 75 %-overlapping
+// frame loads, and half as many CTAs are launched per (short) mel chunk -- same-box A/B: log-mel 6.71 -> 6.32 ms,
+// frame-major log1p-power 5.10 -> 4.75 ms per 8 192 clips.  The bin-major epilogue synchronises the 8 warps of a tile
+// with CTA barriers and keeps GROUPS = 1 (2 CTAs x 8 warps per SM), like the Griffin-Lim kernel, which a 16-warp barrier
+// slows down by 19 %.
+constexpr size_t stft_smem_bytes(int groups) {
+  return 8192 + sizeof(float2) * kTwpCount + 8192 + sizeof(float2) * kScratchPerWarp * kWarpsPerCta * groups;
+}
 
-template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+template <int MODE, int GROUPS>
+__global__ void __launch_bounds__(GROUPS * kWarpsPerCta * 32, GROUPS == 1 ? kCtasPerSm : 1)
 stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips, const int32_t* __restrict__ tile_clip,
             int tile_begin, int tile_end, int hop, int pad_mode, Tables tabs, int layout, void* __restrict__ out_v,
             SplitOut split) {
@@ -96,10 +105,11 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
   float2* s_twp = s_tw1024 + 1024;
   float* s_window = reinterpret_cast<float*>(s_twp + kTwpCount);
   float2* s_scratch_all = reinterpret_cast<float2*>(s_window + kNfft);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_all = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp_all / kWarpsPerCta, warp = warp_all % kWarpsPerCta;   // tile group of this warp, frame inside the tile
   const int kb = mirror_base(lane);
-  float2* scratch = s_scratch_all + warp * kScratchPerWarp;
-  float* s_tile = reinterpret_cast<float*>(s_scratch_all);  // bin-major staging tile aliases the scratch region
+  float2* scratch = s_scratch_all + warp_all * kScratchPerWarp;
+  float* s_tile = reinterpret_cast<float*>(s_scratch_all);  // bin-major staging tile aliases the scratch region (GROUPS == 1)
 
   stage_table(s_tw1024, tabs.tw1024, 512);
   stage_table(s_twp, tabs.twp, kTwpCount / 2);
@@ -108,14 +118,15 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
 
   const int n_out = kBins;  // values per frame in the output
 
-  for (int tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+  const int tile_step = gridDim.x * GROUPS;
+  for (int tile = tile_begin + blockIdx.x * GROUPS + grp; tile < tile_end; tile += tile_step) {
     const int c = __ldg(tile_clip + tile);
     const ClipDesc cd = clips[c];
     const int t0 = (tile - cd.tile_offset) * kWarpsPerCta;
     const int t = t0 + warp;
     const bool active = t < cd.frames;
     {  // pull the audio of this CTA's next tile towards L2 while this one computes
-      const int nt = tile + gridDim.x;
+      const int nt = tile + tile_step;
       if (nt < tile_end && warp == 0) {
         const int c2 = __ldg(tile_clip + nt);
         const ClipDesc cn = clips[c2];
@@ -244,7 +255,7 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
     if (layout == MST_LAYOUT_BIN_MAJOR) {
       // transposed store: clip block is [n_out][T]; the tile's 8 consecutive frames give one 32-byte segment per bin row
       __syncthreads();
-      if (kWarpsPerCta != 8) __trap();
+      if (kWarpsPerCta != 8 || GROUPS != 1) __trap();   // the host never launches this layout with another geometry
       const int nvalid = min(kWarpsPerCta, cd.frames - t0);
       float* blk = out + cd.frame_offset * n_out;
       const bool vec4 = (cd.frames & 3) == 0 && ((cd.frame_offset * n_out) & 3) == 0 && nvalid == kWarpsPerCta &&
@@ -268,6 +279,29 @@ stft_kernel(const float* __restrict__ audio, const ClipDesc* __restrict__ clips,
   }
 }
 
+template <int MODE, int GROUPS>
+static int launch_stft_g(const float* d_audio, const mst_batch* b, int layout, void* d_out, const SplitOut& split,
+                         int tile_begin, int tile_end, const Tables& tabs, cudaStream_t stream) {
+  const size_t smem = stft_smem_bytes(GROUPS);
+  static std::atomic<bool> attr_set[64];  // one flag per device and per (MODE, GROUPS) instantiation
+  int dev = 0;
+  MST_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(MST_ERR_INVALID, "device index %d out of range", dev);
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
+    MST_CUDA_OK(cudaFuncSetAttribute(stft_kernel<MODE, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev].store(true, std::memory_order_release);
+  }
+  int sms = 0;
+  MST_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int n_tiles = tile_end - tile_begin;
+  const int grid = std::min((n_tiles + GROUPS - 1) / GROUPS, (GROUPS == 1 ? kCtasPerSm : 1) * sms);
+  stft_kernel<MODE, GROUPS><<<grid, GROUPS * kWarpsPerCta * 32, smem, stream>>>(
+      d_audio, b->d_clips, b->d_tile_clip, tile_begin, tile_end, b->hop, b->pad_mode, tabs, layout, d_out, split);
+  MST_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return MST_OK;
+}
+
 template <int MODE>
 static int launch_stft(const float* d_audio, const mst_batch* b, int layout, void* d_out, const SplitOut& split,
                        int tile_begin, int tile_end, cudaStream_t stream) {
@@ -275,23 +309,18 @@ static int launch_stft(const float* d_audio, const mst_batch* b, int layout, voi
   int rc = get_tables(&tabs);
   if (rc) return rc;
   if (b->d_window) tabs.window = b->d_window;  // win_length < n_fft: this batch's centre-padded window
-  const size_t smem = kStftSmemBytes;
-  static std::atomic<bool> attr_set[64];  // one flag per device and per MODE instantiation
-  int dev = 0;
-  MST_CUDA_OK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return fail(MST_ERR_INVALID, "device index %d out of range", dev);
-  if (!attr_set[dev].load(std::memory_order_acquire)) {
-    MST_CUDA_OK(cudaFuncSetAttribute(stft_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[dev].store(true, std::memory_order_release);
-  }
-  int sms = 0;
-  MST_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = std::min(tile_end - tile_begin, 2 * sms);
-  stft_kernel<MODE><<<grid, kWarpsPerCta * 32, smem, stream>>>(d_audio, b->d_clips, b->d_tile_clip, tile_begin, tile_end,
-                                                              b->hop, b->pad_mode, tabs, layout, d_out, split);
-  MST_CUDA_OK(cudaGetLastError());
-  count_launch();
-  return MST_OK;
+  // real-valued epilogues in bin-major order synchronise a tile's 8 warps with CTA barriers: 2 CTAs x 8 warps per SM;
+  // everything else: 1 CTA x 16 warps per SM
+  const bool barriers = layout == MST_LAYOUT_BIN_MAJOR &&
+                        (MODE == MST_OUT_MAGNITUDE || MODE == MST_OUT_POWER || MODE == MST_OUT_LOG1P_POWER);
+#ifdef MST_STFT_FORCE_G1   // A/B switch (tools/build_variant.sh): 2 CTAs x 8 warps for every layout
+  const bool force_g1 = true;
+#else
+  const bool force_g1 = false;
+#endif
+  if (barriers || force_g1 || kWarpsPerCta != 8)
+    return launch_stft_g<MODE, 1>(d_audio, b, layout, d_out, split, tile_begin, tile_end, tabs, stream);
+  return launch_stft_g<MODE, 2>(d_audio, b, layout, d_out, split, tile_begin, tile_end, tabs, stream);
 }
 
 }  // namespace mst
