@@ -85,6 +85,7 @@ int64_t mst_batch_total_frames(const mst_batch_t* b);
 int64_t mst_batch_total_samples(const mst_batch_t* b); /* sum of clip lengths */
 int64_t mst_batch_audio_extent(const mst_batch_t* b);  /* max(clip offset + length): floats the audio buffer must hold */
 int mst_batch_device(const mst_batch_t* b);            /* CUDA device the descriptor tables live on */
+int mst_batch_n_fft(const mst_batch_t* b);             /* FFT size: every spectrum of this batch has n_fft/2 + 1 bins */
 int64_t mst_batch_clip_frames(const mst_batch_t* b, int clip);
 int64_t mst_batch_frame_offset(const mst_batch_t* b, int clip); /* prefix sum of frames */
 

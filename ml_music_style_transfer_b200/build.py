@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-CUDA_SOURCES = ["core.cu", "stft.cu", "mel_gemm.cu", "mel_inverse.cu", "griffinlim.cu", "pianoroll.cu", "resample.cu"]
+CUDA_SOURCES = ["core.cu", "stft.cu", "mel_gemm.cu", "mel_inverse.cu", "griffinlim.cu", "generic_fft.cu", "pianoroll.cu", "resample.cu"]
 HEADERS = ["mst_common.cuh", "fft_warp.cuh", "mel_plan.cuh", os.path.join("..", "..", "include", "mst_b200.h")]
 LIB_CUDA = os.path.join(HERE, "libmst_b200.so")
 LIB_OPS = os.path.join(HERE, "libmst_torch_ops.so")

@@ -121,33 +121,35 @@ static int batch_finish(mst_batch* b) {
 }
 
 // librosa: get_window('hann', win_length, fftbins=True) centre-padded to n_fft (util.pad_center), in double
-static std::vector<double> padded_hann(int win_length) {
-  std::vector<double> w((size_t)kNfft, 0.0);
+static std::vector<double> padded_hann(int n_fft, int win_length) {
+  std::vector<double> w((size_t)n_fft, 0.0);
   const double two_pi = 6.283185307179586476925286766559;
-  const int lpad = (kNfft - win_length) / 2;
+  const int lpad = (n_fft - win_length) / 2;
   for (int n = 0; n < win_length; ++n) w[(size_t)lpad + n] = 0.5 - 0.5 * cos(two_pi * (double)n / (double)win_length);
   return w;
 }
 
-// Non-default window length: upload the padded analysis / synthesis windows of this batch.
+// Non-default window length or FFT size: upload the padded analysis / synthesis windows of this batch.
 static int batch_upload_window(mst_batch* b) {
-  if (b->win_length == kNfft) return MST_OK;  // kernels use the per-device default tables
-  const std::vector<double> w = padded_hann(b->win_length);
-  std::vector<float> wf((size_t)kNfft), ws((size_t)kNfft);
-  for (int n = 0; n < kNfft; ++n) {
+  if (b->win_length == kNfft && b->n_fft == kNfft) return MST_OK;  // kernels use the per-device default tables
+  const int n_fft = b->n_fft;
+  const std::vector<double> w = padded_hann(n_fft, b->win_length);
+  std::vector<float> wf((size_t)n_fft), ws((size_t)n_fft);
+  for (int n = 0; n < n_fft; ++n) {
     wf[n] = (float)w[n];
-    ws[n] = wf[n] * (1.0f / 1024.0f);
+    ws[n] = wf[n] * (1.0f / (float)(n_fft / 2));
   }
-  MST_CUDA_OK(cudaMalloc(&b->d_window, sizeof(float) * kNfft));
-  MST_CUDA_OK(cudaMalloc(&b->d_wsyn, sizeof(float) * kNfft));
-  MST_CUDA_OK(cudaMemcpy(b->d_window, wf.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
-  MST_CUDA_OK(cudaMemcpy(b->d_wsyn, ws.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+  MST_CUDA_OK(cudaMalloc(&b->d_window, sizeof(float) * n_fft));
+  MST_CUDA_OK(cudaMalloc(&b->d_wsyn, sizeof(float) * n_fft));
+  MST_CUDA_OK(cudaMemcpy(b->d_window, wf.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+  MST_CUDA_OK(cudaMemcpy(b->d_wsyn, ws.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
   return MST_OK;
 }
 
 static int batch_check(int n_clips, int n_fft, int hop, int win_length, int pad_mode) {
   if (n_clips <= 0) return fail(MST_ERR_INVALID, "n_clips must be positive (got %d)", n_clips);
-  if (n_fft != kNfft) return fail(MST_ERR_UNSUPPORTED, "n_fft=%d unsupported: this build implements n_fft=2048 only", n_fft);
+  if (n_fft != kNfft && !generic_n_fft_ok(n_fft))
+    return fail(MST_ERR_UNSUPPORTED, "n_fft=%d unsupported: n_fft must be a power of two in [64, 16384]", n_fft);
   if (win_length < 1 || win_length > n_fft) return fail(MST_ERR_INVALID, "win_length=%d must be in [1, n_fft]", win_length);
   if (hop <= 0 || hop > n_fft) return fail(MST_ERR_INVALID, "hop=%d must be in [1, n_fft]", hop);
   if (pad_mode != MST_PAD_REFLECT && pad_mode != MST_PAD_CONSTANT) return fail(MST_ERR_INVALID, "bad pad_mode %d", pad_mode);
@@ -220,9 +222,9 @@ int mst_batch_create_from_frames_ex(int n_clips, const int64_t* h_frames, int n_
   // Griffin-Lim needs 1 / window-sum-square per accumulator position (librosa.istft's normalisation,
   // accumulated in float32 frame by frame like librosa's window_sumsquare).  Clips with equal T share one envelope.
   {
-    const std::vector<double> wd = padded_hann(win_length);
-    std::vector<double> wsq(kNfft);
-    for (int n = 0; n < kNfft; ++n) wsq[n] = wd[n] * wd[n];
+    const std::vector<double> wd = padded_hann(n_fft, win_length);
+    std::vector<double> wsq(n_fft);
+    for (int n = 0; n < n_fft; ++n) wsq[n] = wd[n] * wd[n];
     std::vector<int64_t> wss_off((size_t)n_clips);
     std::vector<float> env;
     std::vector<std::pair<int32_t, int64_t>> seen;  // (T, offset)
@@ -232,13 +234,13 @@ int mst_batch_create_from_frames_ex(int n_clips, const int64_t* h_frames, int n_
       for (auto& s : seen) if (s.first == T) { found = s.second; break; }
       if (found < 0) {
         found = (int64_t)env.size();
-        const int64_t n = kNfft + (int64_t)hop * (T - 1);
+        const int64_t n = n_fft + (int64_t)hop * (T - 1);
         const int64_t n_pad = (n + 3) & ~(int64_t)3;
         env.resize(env.size() + (size_t)n_pad, 0.0f);
         float* x = env.data() + found;
         for (int32_t t = 0; t < T; ++t) {
           float* p = x + (int64_t)t * hop;
-          for (int j = 0; j < kNfft; ++j) p[j] = (float)((double)p[j] + wsq[j]);
+          for (int j = 0; j < n_fft; ++j) p[j] = (float)((double)p[j] + wsq[j]);
         }
         const float tiny = 1.17549435e-38f;
         for (int64_t i = 0; i < n; ++i) x[i] = x[i] > tiny ? 1.0f / x[i] : 1.0f;
@@ -248,24 +250,24 @@ int mst_batch_create_from_frames_ex(int n_clips, const int64_t* h_frames, int n_
     }
     // Interior frames (all n_fft/hop overlapping neighbours present) see an envelope that is periodic in hop; fold it
     // into the analysis window once.  Computed like the envelopes above (float32 accumulation in frame order).
-    std::vector<float> wq(kNfft, 0.0f);
+    std::vector<float> wq(n_fft, 0.0f);
     {
-      const int q = (kNfft - 1) / hop;
+      const int q = (n_fft - 1) / hop;
       const int32_t Tq = 2 * q + 1;  // smallest clip with one interior frame (frame q)
-      std::vector<float> x((size_t)kNfft + (size_t)hop * (Tq - 1), 0.0f);
+      std::vector<float> x((size_t)n_fft + (size_t)hop * (Tq - 1), 0.0f);
       for (int32_t t = 0; t < Tq; ++t) {
         float* p = x.data() + (int64_t)t * hop;
-        for (int j = 0; j < kNfft; ++j) p[j] = (float)((double)p[j] + wsq[j]);
+        for (int j = 0; j < n_fft; ++j) p[j] = (float)((double)p[j] + wsq[j]);
       }
       const float tiny = 1.17549435e-38f;
-      for (int j = 0; j < kNfft; ++j) {
+      for (int j = 0; j < n_fft; ++j) {
         const float e = x[(size_t)q * hop + j];
         const float w = (float)wd[j];
         wq[j] = w * (e > tiny ? 1.0f / e : 1.0f);
       }
     }
-    if (cudaMalloc(&b->d_wq, sizeof(float) * kNfft) != cudaSuccess ||
-        cudaMemcpy(b->d_wq, wq.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice) != cudaSuccess ||
+    if (cudaMalloc(&b->d_wq, sizeof(float) * n_fft) != cudaSuccess ||
+        cudaMemcpy(b->d_wq, wq.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMalloc(&b->d_inv_wss, sizeof(float) * env.size()) != cudaSuccess ||
         cudaMemcpy(b->d_inv_wss, env.data(), sizeof(float) * env.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMalloc(&b->d_wss_offset, sizeof(int64_t) * (size_t)n_clips) != cudaSuccess ||
@@ -295,6 +297,7 @@ int64_t mst_batch_total_frames(const mst_batch_t* b) { return b ? b->total_frame
 int64_t mst_batch_total_samples(const mst_batch_t* b) { return b ? b->total_samples : 0; }
 int64_t mst_batch_audio_extent(const mst_batch_t* b) { return b ? b->audio_extent : 0; }
 int mst_batch_device(const mst_batch_t* b) { return b ? b->device : -1; }
+int mst_batch_n_fft(const mst_batch_t* b) { return b ? b->n_fft : 0; }
 int64_t mst_batch_clip_frames(const mst_batch_t* b, int c) { return (b && c >= 0 && c < b->n_clips) ? b->h_clips[c].frames : -1; }
 int64_t mst_batch_frame_offset(const mst_batch_t* b, int c) {
   if (!b || c < 0 || c > b->n_clips) return -1;

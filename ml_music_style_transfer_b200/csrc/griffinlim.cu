@@ -491,6 +491,7 @@ extern "C" {
 
 size_t mst_griffinlim_workspace_bytes_ex(const mst_batch_t* b, int s_layout, int s_is_log1p_power) {
   if (!b) return 0;
+  if (b->n_fft != kNfft) return generic_gl_workspace_bytes(b);
   const size_t spec = (size_t)b->total_frames * kBins;
   const bool needs_copy = s_layout != MST_LAYOUT_FRAME_MAJOR || s_is_log1p_power;  // else the caller's S is used in place
   return align_up((size_t)b->total_frames * kSpecStride * sizeof(float2), 256) +
@@ -515,6 +516,9 @@ int mst_griffinlim_f32(const float* d_S, int s_layout, int s_is_log1p_power, con
   if (workspace_bytes < need) return fail(MST_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
   if (reinterpret_cast<uintptr_t>(d_workspace) & 255) return fail(MST_ERR_INVALID, "workspace must be 256-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (b->n_fft != kNfft)  // general path (generic_fft.cu)
+    return generic_griffinlim(d_S, s_layout, s_is_log1p_power, b, n_iter, momentum, d_init_phase, init_mode, seed, d_y_out,
+                              d_workspace, s);
   Tables tabs;
   int rc = get_tables(&tabs);
   if (rc) return rc;

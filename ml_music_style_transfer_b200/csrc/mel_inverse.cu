@@ -249,6 +249,7 @@ int mst_mel_to_stft_f32(const float* d_mel, int mel_layout, const mst_batch_t* b
   if (!d_mel || !b || !plan || !d_S_out) return fail(MST_ERR_INVALID, "mst_mel_to_stft_f32: null argument");
   if (mel_layout != MST_LAYOUT_FRAME_MAJOR && mel_layout != MST_LAYOUT_BIN_MAJOR) return fail(MST_ERR_INVALID, "bad layout %d", mel_layout);
   if (!(power > 0.0f) || max_iter < 0 || !(tol >= 0.0f)) return fail(MST_ERR_INVALID, "bad power / max_iter / tol");
+  if (b->n_fft != kNfft) return fail(MST_ERR_UNSUPPORTED, "mel inversion is built for n_fft=2048 (batch has n_fft=%d)", b->n_fft);
   if (b->total_frames == 0) return MST_OK;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t smem = ((kBins * kMaxPerBin * 2 + 15) & ~15) + sizeof(float) * kBins * kMaxPerBin +

@@ -53,13 +53,26 @@ struct ClipDesc {        // one per clip, device resident
   int32_t tile_offset;   // prefix sum of ceil(T / kWarpsPerCta)
 };
 
+// ---- general path for n_fft != 2048 (generic_fft.cu) ---------------------------------------------------------------------
+bool generic_n_fft_ok(int n_fft);  // power of two in [64, 16384]
+}  // namespace mst
+struct mst_batch;
+namespace mst {
+int generic_stft(const float* d_audio, const mst_batch* b, int out_mode, int layout, void* d_out, cudaStream_t s);
+int generic_spectral_convergence(const float* d_y, const mst_batch* b, const float* d_S, int s_layout, double* d_num,
+                                 double* d_den, cudaStream_t s);
+size_t generic_gl_workspace_bytes(const mst_batch* b);
+int generic_griffinlim(const float* d_S, int s_layout, int s_is_log1p_power, const mst_batch* b, int n_iter, float momentum,
+                       const float* d_init_phase, int init_mode, uint64_t seed, float* d_y_out, void* d_workspace,
+                       cudaStream_t s);
+
 }  // namespace mst
 
 struct mst_batch {
   int n_clips = 0;
   int n_fft = 0, hop = 0, pad_mode = 0;
   int win_length = 0;                // <= n_fft; the periodic Hann window of this length is centre-padded to n_fft (librosa)
-  float* d_window = nullptr;         // [n_fft] padded analysis window, NULL = the default table (win_length == n_fft)
+  float* d_window = nullptr;         // [n_fft] padded analysis window, NULL = the default table (n_fft == win_length == 2048)
   float* d_wsyn = nullptr;           // [n_fft] padded window / (n_fft / 2): synthesis window with the inverse-FFT scale
   int64_t total_frames = 0, total_samples = 0, total_acc = 0;
   int64_t audio_extent = 0;          // max over clips of sample_offset + length: elements the audio buffer must hold

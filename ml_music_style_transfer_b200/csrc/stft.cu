@@ -335,6 +335,7 @@ int mst_stft_f32(const float* d_audio, const mst_batch_t* b, int out_mode, int l
   if (layout != MST_LAYOUT_FRAME_MAJOR && layout != MST_LAYOUT_BIN_MAJOR) return fail(MST_ERR_INVALID, "bad layout %d", layout);
   SplitOut none{};
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (b->n_fft != kNfft) return generic_stft(d_audio, b, out_mode, layout, d_out, s);  // general path (generic_fft.cu)
   const int nt = b->total_tiles;
   switch (out_mode) {
     case MST_OUT_COMPLEX:
@@ -355,6 +356,7 @@ int mst_spectral_convergence_f32(const float* d_y, const mst_batch_t* b, const f
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   MST_CUDA_OK(cudaMemsetAsync(d_num, 0, sizeof(double) * (size_t)b->n_clips, s));
   MST_CUDA_OK(cudaMemsetAsync(d_den, 0, sizeof(double) * (size_t)b->n_clips, s));
+  if (b->n_fft != kNfft) return generic_spectral_convergence(d_y, b, d_S, s_layout, d_num, d_den, s);
   SplitOut so{};
   so.target = d_S;
   so.num = d_num;
@@ -365,8 +367,32 @@ int mst_spectral_convergence_f32(const float* d_y, const mst_batch_t* b, const f
 int mst_mel_plan_create(const float* W, int n_mels, int n_bins, mst_mel_plan_t** out) {
   if (!W || !out) return fail(MST_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (n_bins != kBins) return fail(MST_ERR_UNSUPPORTED, "mel plan needs n_bins=1025 (n_fft=2048), got %d", n_bins);
   if (n_mels < 1 || n_mels > 256) return fail(MST_ERR_UNSUPPORTED, "n_mels=%d outside [1,256]", n_mels);
+  if (n_bins != kBins) {
+    // another n_fft: the general path projects with the dense float32 filterbank, row by row over its non-zero band
+    if (n_bins < 2 || !generic_n_fft_ok(2 * (n_bins - 1)))
+      return fail(MST_ERR_UNSUPPORTED, "mel plan: n_bins=%d is not 1 + n_fft/2 of a supported n_fft", n_bins);
+    mst_mel_plan* p = new mst_mel_plan();
+    p->n_mels = n_mels; p->n_bins = n_bins;
+    std::vector<int32_t> k_lo((size_t)n_mels, 0), k_hi((size_t)n_mels, 0);
+    for (int m = 0; m < n_mels; ++m) {
+      int lo_k = n_bins, hi_k = 0;
+      for (int k = 0; k < n_bins; ++k)
+        if (W[(size_t)m * n_bins + k] != 0.0f) { lo_k = std::min(lo_k, k); hi_k = k + 1; }
+      k_lo[(size_t)m] = std::min(lo_k, hi_k); k_hi[(size_t)m] = hi_k;
+    }
+    const size_t wb = sizeof(float) * (size_t)n_mels * (size_t)n_bins, ib = sizeof(int32_t) * (size_t)n_mels;
+    if (cudaMalloc(&p->d_dense_w, wb) != cudaSuccess || cudaMalloc(&p->d_k_lo, ib) != cudaSuccess ||
+        cudaMalloc(&p->d_k_hi, ib) != cudaSuccess ||
+        cudaMemcpy(p->d_dense_w, W, wb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->d_k_lo, k_lo.data(), ib, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->d_k_hi, k_hi.data(), ib, cudaMemcpyHostToDevice) != cudaSuccess) {
+      mst_mel_plan_destroy(p);
+      return fail(MST_ERR_CUDA, "mel plan upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = p;
+    return MST_OK;
+  }
   mst_mel_plan* p = new mst_mel_plan();
   p->n_mels = n_mels; p->n_bins = n_bins;
   // band of non-zero mel rows per 64-bin K-slice, padded to multiples of 16 rows (UMMA N granularity at M=128)
@@ -422,6 +448,9 @@ void mst_mel_plan_destroy(mst_mel_plan_t* p) {
   if (!p) return;
   if (p->d_band_hi) cudaFree(p->d_band_hi);
   if (p->d_band_lo) cudaFree(p->d_band_lo);
+  if (p->d_dense_w) cudaFree(p->d_dense_w);
+  if (p->d_k_lo) cudaFree(p->d_k_lo);
+  if (p->d_k_hi) cudaFree(p->d_k_hi);
   delete p;
 }
 
@@ -444,6 +473,8 @@ int mst_stft_mel_f32(const float* d_audio, const mst_batch_t* b, const mst_mel_p
   if (workspace_bytes < mst_stft_mel_workspace_bytes(b, plan))
     return fail(MST_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, mst_stft_mel_workspace_bytes(b, plan));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (b->n_fft != kNfft) return generic_stft_mel(d_audio, b, plan, apply_log1p, layout, d_out, s);
+  if (plan->n_bins != kBins) return fail(MST_ERR_INVALID, "mel plan has %d bins, the batch (n_fft=2048) needs 1025", plan->n_bins);
   const int64_t ring_rows = ring_rows_for_device();
   char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_workspace) + 1023) & ~(uintptr_t)1023);
   SplitOut split;

@@ -92,8 +92,9 @@ at::Tensor stft(const at::Tensor& audio, int64_t batch, int64_t out_mode, int64_
   mst_batch_t* b = as_batch(batch);
   check_batch_audio(b, audio, "audio");
   const int64_t F = mst_batch_total_frames(b);
-  at::Tensor out = out_mode == MST_OUT_COMPLEX ? at::empty({F, 1025}, audio.options().dtype(at::kComplexFloat))
-                                               : at::empty({F * 1025}, audio.options());
+  const int64_t K = mst_batch_n_fft(b) / 2 + 1;
+  at::Tensor out = out_mode == MST_OUT_COMPLEX ? at::empty({F, K}, audio.options().dtype(at::kComplexFloat))
+                                               : at::empty({F * K}, audio.options());
   check(mst_stft_f32(audio.data_ptr<float>(), b, (int)out_mode, (int)layout, out.data_ptr(), cur_stream()), "mst_stft_f32");
   return out;
 }
@@ -247,8 +248,9 @@ at::Tensor griffinlim(const at::Tensor& S, int64_t s_layout, bool s_is_log1p_pow
   mst_batch_t* b = as_batch(batch);
   TORCH_CHECK(mst_batch_device(b) == (int)S.get_device(), "the batch handle was built on cuda:", mst_batch_device(b),
               " but S lives on cuda:", (int)S.get_device());
-  TORCH_CHECK(S.numel() == mst_batch_total_frames(b) * 1025, "S has ", S.numel(), " elements, batch expects ",
-              mst_batch_total_frames(b) * 1025);
+  const int64_t K = mst_batch_n_fft(b) / 2 + 1;
+  TORCH_CHECK(S.numel() == mst_batch_total_frames(b) * K, "S has ", S.numel(), " elements, batch expects ",
+              mst_batch_total_frames(b) * K);
   const float* phase = nullptr;
   if (init_phase.has_value()) {
     want(*init_phase, at::kFloat, "init_phase");
@@ -286,7 +288,7 @@ at::Tensor spectral_convergence(const at::Tensor& y, int64_t batch, const at::Te
   mst_batch_t* b = as_batch(batch);
   check_batch_audio(b, y, "y");
   TORCH_CHECK(S.get_device() == y.get_device(), "S and y live on different devices");
-  TORCH_CHECK(S.numel() == mst_batch_total_frames(b) * 1025, "S does not match the batch");
+  TORCH_CHECK(S.numel() == mst_batch_total_frames(b) * (mst_batch_n_fft(b) / 2 + 1), "S does not match the batch");
   const int64_t n = mst_batch_n_clips(b);
   at::Tensor sums = at::empty({2, n}, y.options().dtype(at::kDouble));
   check(mst_spectral_convergence_f32(y.data_ptr<float>(), b, S.data_ptr<float>(), (int)s_layout, sums.data_ptr<double>(),

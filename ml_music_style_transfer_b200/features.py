@@ -28,11 +28,13 @@ def _pad_code(pad_mode):
 
 
 def _check_window(window, win_length, n_fft):
-    """-> win_length to use.  window='hann' (any win_length <= n_fft, centre-padded like librosa) and n_fft = 2048."""
+    """-> win_length to use.  window='hann' (any win_length <= n_fft, centre-padded like librosa); n_fft = 2048 runs the
+    tuned warp-per-frame kernels, every other power of two in [64, 16384] the general path (csrc/generic_fft.cu)."""
     if window != "hann":
         raise NotImplementedError("only window='hann' is implemented (the reference uses no other)")
-    if n_fft != N_FFT:
-        raise NotImplementedError("n_fft=2048 is the only size the reference uses and the only one built")
+    n_fft = int(n_fft)
+    if n_fft != N_FFT and not (64 <= n_fft <= 16384 and n_fft & (n_fft - 1) == 0):
+        raise NotImplementedError(f"n_fft={n_fft}: n_fft must be a power of two in [64, 16384]")
     if win_length is None:
         return n_fft
     win_length = int(win_length)
@@ -44,8 +46,9 @@ def _check_window(window, win_length, n_fft):
 class ClipBatch:
     """Ragged set of clips inside one audio buffer (``mst_batch_t``).  Chunks may overlap."""
 
-    def __init__(self, handle, n_clips, hop, device):
+    def __init__(self, handle, n_clips, hop, device, n_fft=N_FFT):
         self.handle, self.n_clips, self.hop, self.device = handle, n_clips, hop, device
+        self.n_fft, self.n_bins = int(n_fft), int(n_fft) // 2 + 1
         o = _lib.ops()
         self.total_frames = int(o.batch_total_frames(handle))
         self.total_samples = int(o.batch_total_samples(handle))
@@ -63,14 +66,15 @@ class ClipBatch:
                 # np.pad(mode='reflect') / librosa raise for inputs shorter than the padding: keep the exception type
                 raise ValueError(str(e)) from None
             raise
-        return cls(h, int(offsets.numel()), int(hop), device)
+        return cls(h, int(offsets.numel()), int(hop), device, n_fft)
 
     @classmethod
-    def uniform(cls, n_clips, clip_length, hop, clip_stride=None, pad_mode="reflect", device=None, win_length=None):
+    def uniform(cls, n_clips, clip_length, hop, clip_stride=None, pad_mode="reflect", device=None, win_length=None,
+                n_fft=N_FFT):
         stride = clip_length if clip_stride is None else clip_stride
         offsets = np.arange(n_clips, dtype=np.int64) * stride
         return cls.from_clips(offsets, np.full(n_clips, clip_length, dtype=np.int64), hop, pad_mode, device,
-                              win_length=win_length)
+                              n_fft=n_fft, win_length=win_length)
 
     @classmethod
     def from_frames(cls, frames_per_clip, hop, pad_mode="reflect", device=None, n_fft=N_FFT, win_length=None):
@@ -83,7 +87,7 @@ class ClipBatch:
             if "too short" in str(e):
                 raise ValueError(str(e)) from None
             raise
-        return cls(h, int(frames.numel()), int(hop), device)
+        return cls(h, int(frames.numel()), int(hop), device, n_fft)
 
     def clip_frames(self, c):
         return int(_lib.ops().batch_clip_frames(self.handle, c))
@@ -113,7 +117,7 @@ class MelPlan:
     _cache = {}
 
     def __init__(self, weights, device):
-        self.weights = weights  # CPU float32 (n_mels, 1025)
+        self.weights = weights  # CPU float32 (n_mels, 1 + n_fft/2)
         self.n_mels = int(weights.shape[0])
         self.device = device
         self.handle = _lib.ops().mel_plan_create(weights.contiguous(), device.index)
@@ -186,22 +190,23 @@ def melspectrogram_batch(audio, batch, plan, log1p=False, layout=FRAME_MAJOR):
 
 
 def stft(y, n_fft=N_FFT, hop_length=None, win_length=None, window="hann", center=True, pad_mode="reflect"):
-    """librosa.stft drop-in for one clip: complex64 (1025, T), Fortran-ordered like librosa's result."""
+    """librosa.stft drop-in for one clip: complex64 (1 + n_fft/2, T), Fortran-ordered like librosa's result."""
     win_length = _check_window(window, win_length, n_fft)
     if not center:
         raise NotImplementedError("center=False is not used by the reference")
     hop = win_length // 4 if hop_length is None else int(hop_length)
     a, was_np = _to_device_audio(y)
-    with ClipBatch.uniform(1, a.numel(), hop, pad_mode=pad_mode, device=a.device, win_length=win_length) as b:
-        out = stft_batch(a, b, "complex")  # [T][1025] memory; its transpose view == librosa's Fortran-ordered (1025, T)
+    with ClipBatch.uniform(1, a.numel(), hop, pad_mode=pad_mode, device=a.device, win_length=win_length, n_fft=n_fft) as b:
+        out = stft_batch(a, b, "complex")  # [T][K] memory; its transpose view == librosa's Fortran-ordered (K, T)
     return to_numpy(out).T if was_np else out.t()
 
 
-def spectrogram(y, hop_length, out="log1p_power", pad_mode="reflect"):
-    """(1025, T) float32 epilogue of the STFT for one clip (Fortran-ordered view)."""
+def spectrogram(y, hop_length, out="log1p_power", pad_mode="reflect", n_fft=N_FFT):
+    """(1 + n_fft/2, T) float32 epilogue of the STFT for one clip (Fortran-ordered view)."""
+    _check_window("hann", None, n_fft)
     a, was_np = _to_device_audio(y)
-    with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device) as b:
-        o = stft_batch(a, b, out).view(b.total_frames, N_BINS)
+    with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device, n_fft=n_fft) as b:
+        o = stft_batch(a, b, out).view(b.total_frames, b.n_bins)
     return to_numpy(o).T if was_np else o.t()
 
 
@@ -211,7 +216,7 @@ def melspectrogram(y=None, sr=22050, n_fft=N_FFT, hop_length=512, n_mels=128, fm
     _check_window("hann", None, n_fft)
     a, was_np = _to_device_audio(y)
     plan = MelPlan.get(sr, n_fft, n_mels, fmin, fmax, a.device)
-    with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device) as b:
+    with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device, n_fft=n_fft) as b:
         o = melspectrogram_batch(a, b, plan, log1p=log1p, layout=BIN_MAJOR).view(n_mels, b.total_frames)
     return to_numpy(o) if was_np else o
 
@@ -232,7 +237,8 @@ def griffinlim_batch(S, batch, n_iter=32, momentum=0.99, init_phase=None, init="
 
 def griffinlim(S, n_iter=32, hop_length=None, win_length=None, window="hann", momentum=0.99, init="random",
                random_state=None, init_phase=None, pad_mode="reflect"):
-    """librosa.griffinlim drop-in for one (1025, T) magnitude spectrogram -> float32 waveform of hop*(T-1) samples.
+    """librosa.griffinlim drop-in for one (1 + n_fft/2, T) magnitude spectrogram -> float32 waveform of hop*(T-1) samples
+    (n_fft is inferred from the bin count, as librosa does).
 
     ``random_state=int`` reproduces librosa's ``RandomState(seed).rand(*S.shape)`` initial phase exactly (drawn on the
     host); ``init_phase`` supplies the uniform [0,1) field directly; with ``random_state=None`` the phase comes from the
@@ -243,25 +249,26 @@ def griffinlim(S, n_iter=32, hop_length=None, win_length=None, window="hann", mo
     device = _lib.require_cuda(None if was_np else S.device)
     if was_np:
         S = torch.from_numpy(np.ascontiguousarray(S, dtype=np.float32)).to(device)
-    if S.dim() != 2 or S.shape[0] != N_BINS:
-        raise ValueError(f"S must be (1025, T); got {tuple(S.shape)}")
+    if S.dim() != 2 or S.shape[0] < 2:
+        raise ValueError(f"S must be (1 + n_fft/2, T); got {tuple(S.shape)}")
     n_fft = 2 * (S.shape[0] - 1)
+    n_bins = int(S.shape[0])
     win_length = _check_window(window, win_length, n_fft)
     hop = win_length // 4 if hop_length is None else int(hop_length)
     T = int(S.shape[1])
     if init_phase is None and init == "random" and isinstance(random_state, (int, np.integer)):
-        init_phase = np.random.RandomState(int(random_state)).rand(N_BINS, T)
+        init_phase = np.random.RandomState(int(random_state)).rand(n_bins, T)
     if init_phase is not None and not isinstance(init_phase, torch.Tensor):
         init_phase = torch.from_numpy(np.ascontiguousarray(init_phase, dtype=np.float32)).to(device)
-    # a (1025,T) tensor whose memory is [T][1025] (librosa's Fortran order) is consumed without a transpose
-    if S.stride() == (1, N_BINS) and (init_phase is None or init_phase.stride() == (1, N_BINS)):
+    # a (K,T) tensor whose memory is [T][K] (librosa's Fortran order) is consumed without a transpose
+    if S.stride() == (1, n_bins) and (init_phase is None or init_phase.stride() == (1, n_bins)):
         layout, S_flat = FRAME_MAJOR, S.t()
         ph = None if init_phase is None else init_phase.t()
     else:
         layout, S_flat = BIN_MAJOR, S.contiguous()
         ph = None if init_phase is None else init_phase.to(torch.float32).contiguous()
     seed = int(np.random.randint(0, 2 ** 31 - 1))
-    with ClipBatch.from_frames([T], hop, pad_mode=pad_mode, device=device, win_length=win_length) as b:
+    with ClipBatch.from_frames([T], hop, pad_mode=pad_mode, device=device, n_fft=n_fft, win_length=win_length) as b:
         y = griffinlim_batch(S_flat.to(torch.float32), b, n_iter, momentum, ph, init, seed, layout)
     return to_numpy(y) if was_np else y
 
@@ -278,7 +285,8 @@ def mel_to_stft(M, sr=22050, n_fft=N_FFT, power=2.0, fmin=0.0, fmax=None, max_it
     ``nnls(mel_basis, M) ** (1 / power)``.  Same start point as librosa.util.nnls (clipped least squares); the NNLS
     problem of every frame is then solved to ``tol`` (relative residual) instead of stopping where L-BFGS-B's scaled
     projected-gradient test stops, so the residual ||mel_basis @ S**power - M|| is <= librosa's."""
-    _check_window("hann", None, n_fft)
+    if int(n_fft) != N_FFT:
+        raise NotImplementedError("mel inversion is built for n_fft=2048 (the size the reference uses)")
     was_np = not isinstance(M, torch.Tensor)
     device = _lib.require_cuda(None if was_np else M.device)
     if was_np:
@@ -321,8 +329,10 @@ def spectral_convergence(S, y, hop_length, pad_mode="reflect"):
     a, _ = _to_device_audio(y)
     if not isinstance(S, torch.Tensor):
         S = torch.from_numpy(np.ascontiguousarray(S, dtype=np.float32)).to(a.device)
-    with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device) as b:
-        if S.shape != (N_BINS, b.total_frames):
-            raise ValueError(f"S must be (1025, {b.total_frames}) for this waveform; got {tuple(S.shape)}")
+    n_fft = 2 * (int(S.shape[0]) - 1)
+    _check_window("hann", None, n_fft)
+    with ClipBatch.uniform(1, a.numel(), int(hop_length), pad_mode=pad_mode, device=a.device, n_fft=n_fft) as b:
+        if S.shape != (b.n_bins, b.total_frames):
+            raise ValueError(f"S must be ({b.n_bins}, {b.total_frames}) for this waveform; got {tuple(S.shape)}")
         sc = spectral_convergence_batch(a, b, S.to(torch.float32), BIN_MAJOR)
     return float(sc[0])

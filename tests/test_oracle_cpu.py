@@ -294,8 +294,9 @@ def test_batch_argument_errors(built_libs):
     out = ctypes.c_void_p()
     off = (ctypes.c_int64 * 1)(0)
     ln = (ctypes.c_int64 * 1)(4096)
-    assert lib.mst_batch_create(1, off, ln, 1024, 256, 0, ctypes.byref(out)) == -2  # MST_ERR_UNSUPPORTED
-    assert b"2048" in lib.mst_last_error()
+    for n_fft in (1000, 32, 32768):   # not a power of two / outside [64, 16384] (checked before any CUDA call)
+        assert lib.mst_batch_create(1, off, ln, n_fft, 256, 0, ctypes.byref(out)) == -2  # MST_ERR_UNSUPPORTED
+        assert b"power of two" in lib.mst_last_error()
     ln[0] = 1000
     assert lib.mst_batch_create(1, off, ln, 2048, 256, 0, ctypes.byref(out)) == -1  # too short for reflect
 
