@@ -15,8 +15,10 @@
  *     default stream); nothing here synchronises the device except *_create / *_destroy;
  *   - return value: 0 = MST_OK, negative = error, text via mst_last_error() (thread-local);
  *   - there is no CPU fallback: without a CUDA device every compute entry returns MST_ERR_CUDA.
- *   - n_fft is fixed at 2048 (the only value the reference uses: preprocess.py:25,
- *     inference.py:105); other values return MST_ERR_UNSUPPORTED.
+ *   - n_fft = 2048 (the only value the reference uses: preprocess.py:25, inference.py:105) runs the tuned
+ *     warp-per-frame kernels; every other power of two in [64, 16384] runs the general path (one CTA per
+ *     frame, shared-memory FFT) behind the same entry points, every spectrum then has n_fft/2 + 1 bins;
+ *     anything else returns MST_ERR_UNSUPPORTED.  Mel inversion is n_fft = 2048 only.
  */
 #ifndef MST_B200_H_
 #define MST_B200_H_
