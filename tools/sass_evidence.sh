@@ -20,5 +20,5 @@ kernel() {  # $1 = mangled-name regex, $2 = output file, $3 = grep pattern for t
 }
 kernel "mel_gemm_kernel" sass_mel_gemm.txt "UTC[A-Z]*MMA|UTMALDG|UBLKCP|LDTM|STTM|UTCBAR|SYNCS|UTCATOM|TCGEN|UGETNEXT|R2UR"
 kernel "gl_kernelILb0ELb0" sass_gl_kernel.txt "FFMA2|FADD2|FMUL2|LDGSTS|REDG|RED\.|SHFL|MUFU"
-kernel "stft_kernelILi3" sass_stft_log1p.txt "FFMA2|FADD2|FMUL2|SHFL|MUFU|LDG\.E\.64"
+kernel "mst11stft_kernelILi3" sass_stft_log1p.txt "FFMA2|FADD2|FMUL2|SHFL|MUFU|LDG\.E\.64"
 kernel "upsample_kernelIaLi2" sass_upsample.txt "STG\.E\.128|PRMT|SHFL|VOTE|LOP3"
