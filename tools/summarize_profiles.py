@@ -12,8 +12,10 @@ launches, rep, tag = sys.argv[1:4]
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
-# ---- launch list: per-kernel share of the step --------------------------------------------------------------------
-rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
+# ---- launch list: per-kernel share of the step ("-" = none, summarise the full capture only) -------------------------
+rows = [] if launches == "-" else [r for r in csv.reader(open(launches)) if len(r) > 5]
+if not rows:
+    rows = [["Kernel Name", "Metric Value", "Metric Unit", "", "", ""], ["", "x", "ns", "", "", ""]]
 hdr_i = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 hdr = rows[hdr_i]
 kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -32,12 +34,13 @@ for r in rows[hdr_i + 1:]:
 unit = rows[hdr_i + 1][hdr.index("Metric Unit")]
 scale = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "msecond": 1.0, "ms": 1.0, "nsecond": 1e-6}.get(unit, 1e-6)
 total = sum(a[1] for a in agg.values())
-with open(os.path.join(out_dir, f"{tag}_launch_shares.csv"), "w") as f:
-    w = csv.writer(f)
-    w.writerow(["kernel", "launches", "total_ms", "share_pct"])
-    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        w.writerow([k, n, f"{t * scale:.3f}", f"{100 * t / total:.2f}"])
-subprocess.run(["cp", launches, os.path.join(out_dir, f"{tag}_launches.csv")], check=True)
+if launches != "-":
+    with open(os.path.join(out_dir, f"{tag}_launch_shares.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel", "launches", "total_ms", "share_pct"])
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            w.writerow([k, n, f"{t * scale:.3f}", f"{100 * t / total:.2f}"])
+    subprocess.run(["cp", launches, os.path.join(out_dir, f"{tag}_launches.csv")], check=True)
 
 # ---- full capture: key metrics per kernel --------------------------------------------------------------------------
 rr = []
