@@ -5,6 +5,7 @@
 //
 // Replaces librosa.stft + np.log1p(np.abs(.)**2) (reference preprocessing/preprocess.py:47-57) and, together with
 // mel_gemm.cu, librosa.feature.melspectrogram (reference tests/plot_spec.py:20).
+#include <stdlib.h>
 #include <algorithm>
 #include <atomic>
 #include <vector>
@@ -454,16 +455,34 @@ void mst_mel_plan_destroy(mst_mel_plan_t* p) {
   delete p;
 }
 
-// Ring of split-precision power-spectrum rows between the STFT kernel and the projection kernel: one full wave of
-// 128-frame projection tiles (n_SM x 128 rows x 2 x 2176 B ~ 82 MB on B200), sized to stay resident in the 126 MB L2.
+// Ring of split-precision power-spectrum rows between the STFT kernel and the projection kernel.  Round 1 sized it as ONE
+// wave of 128-frame projection tiles (n_SM x 128 rows x 2 x 2176 B ~ 82 MB) so that it stays in the 126 MB L2; measured in
+// round 2 (tools/ab_mel.py, same box, 8 192 clips): 1 / 2 / 4 / 8 waves per chunk = 6.28 / 5.68 / 5.39 / 5.27 ms.  With one
+// tile per CTA the projection kernel never overlaps a tile's epilogue with the next tile's MMAs (its two TMEM accumulators
+// exist for exactly that) and pays its filterbank load and pipeline fill per 128 frames; the extra HBM round trip of a
+// ring that no longer fits in L2 (2 x 4.3 KB per frame) is far below what either kernel needs in time.  Default: 8 waves,
+// never more rows than the batch has frames.
+#ifndef MST_MEL_RING_WAVES
+#define MST_MEL_RING_WAVES 8
+#endif
 static int64_t ring_rows_for_device() {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return (int64_t)sms * 128;
+  static const int waves = [] {   // A/B knob: MST_MEL_RING_WAVES (env) = projection tiles per CTA and ring chunk
+    const char* e = getenv("MST_MEL_RING_WAVES");
+    const int w = e ? atoi(e) : MST_MEL_RING_WAVES;
+    return w >= 1 && w <= 16 ? w : MST_MEL_RING_WAVES;
+  }();
+  return (int64_t)sms * 128 * waves;
 }
 
-size_t mst_stft_mel_workspace_bytes(const mst_batch_t*, const mst_mel_plan_t*) {
-  return 2 * (size_t)ring_rows_for_device() * kSpecPad * sizeof(__nv_bfloat16) + 1024;
+static int64_t ring_rows_for_batch(const mst_batch_t* b) {
+  const int64_t need = b ? ((b->total_frames + 127) / 128) * 128 : 0;  // whole projection tiles
+  return std::max<int64_t>(128, std::min(ring_rows_for_device(), need));
+}
+
+size_t mst_stft_mel_workspace_bytes(const mst_batch_t* b, const mst_mel_plan_t*) {
+  return 2 * (size_t)ring_rows_for_batch(b) * kSpecPad * sizeof(__nv_bfloat16) + 1024;
 }
 
 int mst_stft_mel_f32(const float* d_audio, const mst_batch_t* b, const mst_mel_plan_t* plan, int apply_log1p, int layout,
@@ -475,7 +494,7 @@ int mst_stft_mel_f32(const float* d_audio, const mst_batch_t* b, const mst_mel_p
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (b->n_fft != kNfft) return generic_stft_mel(d_audio, b, plan, apply_log1p, layout, d_out, s);
   if (plan->n_bins != kBins) return fail(MST_ERR_INVALID, "mel plan has %d bins, the batch (n_fft=2048) needs 1025", plan->n_bins);
-  const int64_t ring_rows = ring_rows_for_device();
+  const int64_t ring_rows = ring_rows_for_batch(b);
   char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_workspace) + 1023) & ~(uintptr_t)1023);
   SplitOut split;
   split.hi = reinterpret_cast<__nv_bfloat16*>(ws);
