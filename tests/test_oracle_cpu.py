@@ -378,3 +378,35 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "audio-s/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+# ---- pins at other FFT sizes / window lengths (tests/golden/make_golden3.py: torch.stft, torch.istft, torchaudio) ----------
+@pytest.mark.parametrize("n_fft,hop,win", [(1024, 256, 1024), (4096, 1024, 4096), (512, 100, 512), (1024, 256, 800),
+                                           (2048, 512, 1200)])
+def test_oracle_other_nfft_matches_torch_golden(n_fft, hop, win):
+    g = np.load(os.path.join(GOLD, "other_nfft_pins.npz"))
+    tag = f"{n_fft}_{hop}_{win}"
+    D = ostft.stft(g["y"], n_fft, hop, win_length=win)
+    ref = g[f"stft_{tag}"]
+    assert D.shape == ref.shape == (n_fft // 2 + 1, 1 + 5000 // hop)
+    assert relerr(D, ref) < 3e-7
+    if f"istft_{tag}" in g.files:
+        y = ostft.istft(ref, hop, win_length=win)
+        r = g[f"istft_{tag}"]
+        assert y.shape == r.shape and np.abs(y - r).max() < 3e-6
+    if f"gl6_{tag}" in g.files:
+        w = ogl.griffinlim(np.abs(ref).astype(np.float32), 6, hop, win_length=win, init_phase=None)
+        r = g[f"gl6_{tag}"]
+        assert np.abs(w - r[:len(w)]).max() < 2e-4 * np.abs(r).max()
+
+
+@pytest.mark.parametrize("sr,n_fft,n_mels", [(22050, 1024, 80), (44100, 4096, 128)])
+def test_oracle_mel_filterbank_other_nfft(sr, n_fft, n_mels, built_libs):
+    ref = np.load(os.path.join(GOLD, "other_nfft_pins.npz"))[f"fb_{sr}_{n_fft}_{n_mels}"]
+    W = omel.mel_filterbank(sr, n_fft, n_mels)
+    assert W.shape == ref.shape and np.abs(W - ref).max() / np.abs(ref).max() < 1e-5
+    lib = ctypes.CDLL(built_libs[0])
+    Wc = np.zeros_like(W)
+    assert lib.mst_mel_filterbank_f32(sr, n_fft, n_mels, ctypes.c_double(0.0), ctypes.c_double(0.0),
+                                      Wc.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert np.array_equal(Wc, W)
