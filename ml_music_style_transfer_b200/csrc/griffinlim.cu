@@ -226,6 +226,16 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
   const int t0 = (tile - cd.tile_offset) * kWarpsPerCta;
   const int t = t0 + warp;
   const bool active = t < cd.frames;
+  // Barrier B2 ("every warp is done reading the slots of the previous tile's overlap-add") is executed exactly once per
+  // warp and tile, at the latest point before this warp writes its scratch tile again: interior frames first request
+  // their 32 accumulator loads, so the wait overlaps the load latency.
+#ifdef MST_GL_B2_EARLY
+  __syncthreads();
+  constexpr bool kLateB2 = false;
+#else
+  constexpr bool kLateB2 = true;
+#endif
+    if (!active && kLateB2) __syncthreads();
     if (active) {
       const int64_t frame = cd.frame_offset + t;
       const float* Srow = P.S + frame * kBins;
@@ -235,6 +245,7 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
       float2 y[32];
       float2 mid = make_float2(0.0f, 0.0f);
       if (INIT) {
+        if (kLateB2) __syncthreads();
         // y_0 = istft(S * exp(2*pi*i*u)).  All target magnitudes are requested first (33 loads in flight per lane), the
         // phases are computed while they arrive: the one-load-one-use form left a DRAM round trip exposed per bin
         // (ncu: long_scoreboard 5.7 cycles per issued instruction in this launch).
@@ -278,12 +289,21 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
           // interior frame: the envelope is periodic in hop and pre-multiplied into the analysis window
           const float2* a2 = reinterpret_cast<const float2*>(acc + base + kHalf) + lane;
           const float2* w2 = reinterpret_cast<const float2*>(s_wq) + lane;
+          if (kLateB2) {
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const float2 a = COHERENT ? __ldcg(a2 + 32 * r) : a2[32 * r];
-            v[r] = pk_mul(a, w2[32 * r]);
+            for (int r = 0; r < 32; ++r) v[r] = COHERENT ? __ldcg(a2 + 32 * r) : a2[32 * r];
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = pk_mul(v[r], w2[32 * r]);
+          } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const float2 a = COHERENT ? __ldcg(a2 + 32 * r) : a2[32 * r];
+              v[r] = pk_mul(a, w2[32 * r]);
+            }
           }
         } else {
+          if (kLateB2) __syncthreads();
           // edge frame (rare): stage through this warp's scratch with a compact loop
           const float* iw = P.inv_wss + __ldg(P.wss_off + c);
           float* sf = reinterpret_cast<float*>(scratch);
@@ -355,7 +375,6 @@ __device__ __forceinline__ void gl_tile(const GlParams& P, const GlSmem& m, int 
     }
     __syncthreads();
     overlap_add_tile(reinterpret_cast<const float*>(s_scratch_all), cd, t0, P.hop, P.hop_shift, P.acc_out, P.acc_zero);
-    __syncthreads();
 }
 
 template <bool INIT, bool FIRST>
