@@ -368,6 +368,7 @@ def run_ours(args):
         x44 = torch.randn(64 * 8 * 44100, device=device) * 0.1           # 64 clips x 8 s at 44.1 kHz, one buffer
         t_rs = med(timed(lambda: L.ops().resample(x44, 44100, 22050), 5))
         taps = 2 * 64 * 2                                                 # both wings, 64 zero crossings, ratio 1/2
+        t_rs48 = med(timed(lambda: L.ops().resample(x44, 48000, 44100), 5))  # rational ratio 160/147: per-phase weight tables
         n_ch, step_, clen = 256, 131072, 219904                           # preprocess.py:66-67 chunk geometry
         a_repo = torch.randn((n_ch - 1) * step_ + clen, device=device) * 0.1
         b_repo = F.ClipBatch.uniform(n_ch, clen, 256, clip_stride=step_, device=device)
@@ -376,6 +377,7 @@ def run_ours(args):
         extras = {
             "resample_44k1_to_22k05": {"ms": t_rs, "audio_s_per_s": 64 * 8 / (t_rs * 1e-3),
                                        "gflops": 2.0 * taps * 2 * (x44.numel() // 2) / (t_rs * 1e-3) / 1e9},
+            "resample_48k_to_44k1": {"ms": t_rs48, "audio_s_per_s": x44.numel() / 48000 / (t_rs48 * 1e-3)},
             "reference_geometry_log1p_power": {"chunks": n_ch, "ms": t_repo, "audio_s_per_s": n_ch * clen / 44100 / (t_repo * 1e-3),
                                                "hbm_frac": repo_bytes / (t_repo * 1e-3) / 1e9 / hbm_peak,
                                                "note": "44.1 kHz, hop 256, 219904-sample chunks every 131072, bin-major stack"}}

@@ -2,10 +2,13 @@
 // (reference preprocessing/preprocess.py:106, model/inference.py:54, tests/test_griffinlim.py:16).
 // Band-limited sinc interpolation exactly as resampy 0.2.2 'kaiser_best' evaluates it (librosa 0.8's default
 // res_type): half-window rolloff*sinc(rolloff*t)*kaiser(beta) tabulated 512 times per zero crossing over 64 zero
-// crossings, linear interpolation between table entries, left wing then right wing.  General ratios: one thread per
-// output sample, the 256 KB (value, delta) table L2 resident; exact halving of the rate takes resample_half_kernel.  Index arithmetic is done in double so that table offsets match
+// crossings, linear interpolation between table entries, left wing then right wing.  Three kernels: exact halving of the
+// rate -> resample_half_kernel (one symmetric FIR); rational ratios p/q with q <= 2048 -> resample_phase_kernel (tap weights
+// precomputed per phase); anything else -> resample_kernel (one thread per output interpolating the 256 KB L2-resident
+// (value, delta) table).  Index arithmetic is done in double so that table offsets match
 // the Python evaluation bit for bit.
 #include <math.h>
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -50,6 +53,62 @@ __global__ void resample_kernel(const float* __restrict__ x, int64_t n_in, float
       const float2 w = __ldg(table + offset + k * index_step);
       acc = fmaf(fmaf(eta, w.y, w.x), __ldg(x + n + k + 1), acc);
     }
+    y[t] = acc;
+  }
+}
+
+// Rational ratios sr_in / sr_out = p / q with a small q (48 -> 44.1 kHz: 160 / 147; 44.1 -> 16 kHz: 441 / 160; any integer
+// up-sampling factor ...): output t sits at input position t*p/q, so only q distinct table phases exist.  The interpolated
+// tap weights of every phase (left wing then right wing, resampy's order) are evaluated once on the host with the same
+// float32 fma as resample_kernel and stored as one 16-byte-aligned row per phase; a thread then runs
+// acc = fma(w[j], x[..], acc) over its row with 128-bit weight loads -- no per-tap table lookup, no interpolation and no
+// index arithmetic in the loop.  Summation order is the reference's.
+struct PhaseGeom {
+  int64_t p, q;
+  int row;        // floats per weight row (multiple of 4): [0, max_left) left wing, [max_left, max_left + max_right) right wing
+  int max_left;   // multiple of 4
+};
+
+__global__ void __launch_bounds__(256)
+resample_phase_kernel(const float* __restrict__ x, int64_t n_in, float* __restrict__ y, int64_t n_out, int64_t n_fix,
+                      const float* __restrict__ W, const int2* __restrict__ lims, PhaseGeom g) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_fix; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t >= n_out) {  // librosa util.fix_length: zero padding up to ceil(n * ratio)
+      y[t] = 0.0f;
+      continue;
+    }
+    const int64_t tp = t * g.p;
+    const int64_t n = tp / g.q;
+    const int phase = (int)(tp - n * g.q);
+    const int2 lim = __ldg(lims + phase);
+    const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)phase * g.row);
+    float acc = 0.0f;
+    // left wing: x[n - i], i = 0 .. min(n + 1, lim.x) - 1
+    const int i_max = (int)(n + 1 < lim.x ? n + 1 : lim.x);
+    const float* xl = x + n;
+    int i = 0;
+    for (; i + 4 <= i_max; i += 4) {
+      const float4 w = __ldg(w4 + (i >> 2));
+      acc = fmaf(w.x, __ldg(xl - i), acc);
+      acc = fmaf(w.y, __ldg(xl - i - 1), acc);
+      acc = fmaf(w.z, __ldg(xl - i - 2), acc);
+      acc = fmaf(w.w, __ldg(xl - i - 3), acc);
+    }
+    for (; i < i_max; ++i) acc = fmaf(__ldg(W + (size_t)phase * g.row + i), __ldg(xl - i), acc);
+    // right wing: x[n + 1 + k], k = 0 .. min(n_in - n - 1, lim.y) - 1
+    const int64_t avail = n_in - n - 1;
+    const int k_max = (int)(avail < lim.y ? (avail > 0 ? avail : 0) : lim.y);
+    const float* xr = x + n + 1;
+    const float4* r4 = w4 + (g.max_left >> 2);
+    int k = 0;
+    for (; k + 4 <= k_max; k += 4) {
+      const float4 w = __ldg(r4 + (k >> 2));
+      acc = fmaf(w.x, __ldg(xr + k), acc);
+      acc = fmaf(w.y, __ldg(xr + k + 1), acc);
+      acc = fmaf(w.z, __ldg(xr + k + 2), acc);
+      acc = fmaf(w.w, __ldg(xr + k + 3), acc);
+    }
+    for (; k < k_max; ++k) acc = fmaf(__ldg(W + (size_t)phase * g.row + g.max_left + k), __ldg(xr + k), acc);
     y[t] = acc;
   }
 }
@@ -132,7 +191,68 @@ static double bessel_i0(double x) {
 static std::mutex g_rs_mutex;
 static std::map<std::tuple<int, int, int>, float2*> g_rs_tables;  // (device, sr_in, sr_out)
 
-static int get_rs_table(int sr_in, int sr_out, const float2** out) {
+struct PhaseTable {
+  bool usable = false;
+  PhaseGeom geom{};
+  float* d_w = nullptr;
+  int2* d_lims = nullptr;
+};
+static std::map<std::tuple<int, int, int>, PhaseTable> g_rs_phase;  // (device, sr_in, sr_out)
+constexpr int64_t kRsMaxPhases = 2048;
+constexpr size_t kRsMaxPhaseFloats = (size_t)1 << 21;  // 8 MB of weights at most (L2 resident)
+
+static int64_t gcd64(int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; }
+
+// Per-phase tap weights from the host copy of the (value, delta) table.
+static int build_phase_table(const std::vector<float2>& tab, int sr_in, int sr_out, PhaseTable* pt) {
+  const int64_t g = gcd64(sr_in, sr_out);
+  const int64_t p = sr_in / g, q = sr_out / g;
+  const double ratio = (double)sr_out / (double)sr_in;
+  const double scale = ratio < 1.0 ? ratio : 1.0;
+  const int index_step = (int)(scale * (double)kRsTable);
+  if (q > kRsMaxPhases || index_step < 1) return MST_OK;  // not usable: the per-output kernel handles it
+  const int max_lim = (kRsWin + index_step - 1) / index_step + 1;
+  const int max_side = (max_lim + 3) & ~3;
+  const int row = 2 * max_side;
+  if ((size_t)q * (size_t)row > kRsMaxPhaseFloats) return MST_OK;
+  std::vector<float> w((size_t)q * (size_t)row, 0.0f);
+  std::vector<int2> lims((size_t)q);
+  for (int64_t ph = 0; ph < q; ++ph) {
+    const double pos = (double)ph / (double)q;  // fractional input position of this phase
+    float* wl = w.data() + (size_t)ph * row;
+    float* wr = wl + max_side;
+    double frac = scale * pos;
+    double index_frac = frac * (double)kRsTable;
+    int offset = (int)index_frac;
+    float eta = (float)(index_frac - (double)offset);
+    int lim = (kRsWin - offset) / index_step;
+    for (int i = 0; i < lim; ++i) {
+      const float2 t = tab[(size_t)offset + (size_t)i * index_step];
+      wl[i] = fmaf(eta, t.y, t.x);
+    }
+    lims[(size_t)ph].x = lim;
+    frac = scale - frac;
+    index_frac = frac * (double)kRsTable;
+    offset = (int)index_frac;
+    eta = (float)(index_frac - (double)offset);
+    lim = (kRsWin - offset) / index_step;
+    for (int k = 0; k < lim; ++k) {
+      const float2 t = tab[(size_t)offset + (size_t)k * index_step];
+      wr[k] = fmaf(eta, t.y, t.x);
+    }
+    lims[(size_t)ph].y = lim;
+    if (lims[(size_t)ph].x > max_side || lims[(size_t)ph].y > max_side) return fail(MST_ERR_INVALID, "resampler phase table overflow");
+  }
+  MST_CUDA_OK(cudaMalloc(&pt->d_w, sizeof(float) * w.size()));
+  MST_CUDA_OK(cudaMalloc(&pt->d_lims, sizeof(int2) * lims.size()));
+  MST_CUDA_OK(cudaMemcpy(pt->d_w, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+  MST_CUDA_OK(cudaMemcpy(pt->d_lims, lims.data(), sizeof(int2) * lims.size(), cudaMemcpyHostToDevice));
+  pt->geom.p = p; pt->geom.q = q; pt->geom.row = row; pt->geom.max_left = max_side;
+  pt->usable = true;
+  return MST_OK;
+}
+
+static int get_rs_table(int sr_in, int sr_out, const float2** out, const PhaseTable** phase_out) {
   int dev = 0;
   MST_CUDA_OK(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(g_rs_mutex);
@@ -159,8 +279,15 @@ static int get_rs_table(int sr_in, int sr_out, const float2** out) {
     MST_CUDA_OK(cudaMalloc(&d, sizeof(float2) * tab.size()));
     MST_CUDA_OK(cudaMemcpy(d, tab.data(), sizeof(float2) * tab.size(), cudaMemcpyHostToDevice));
     it = g_rs_tables.emplace(key, d).first;
+    PhaseTable pt;
+    if (sr_in != 2 * sr_out) {  // exact halving has its own kernel
+      const int rc = build_phase_table(tab, sr_in, sr_out, &pt);
+      if (rc) return rc;
+    }
+    g_rs_phase.emplace(key, pt);
   }
   *out = it->second;
+  *phase_out = &g_rs_phase[key];
   return MST_OK;
 }
 
@@ -203,7 +330,8 @@ int mst_resample_f32(const float* d_in, int64_t n_in, int sr_in, int sr_out, flo
   const int index_step = (int)(scale * (double)kRsTable);
   if (index_step < 1) return fail(MST_ERR_UNSUPPORTED, "down-sampling ratio %g too small", ratio);
   const float2* table = nullptr;
-  int rc = get_rs_table(sr_in, sr_out, &table);
+  const PhaseTable* phases = nullptr;
+  int rc = get_rs_table(sr_in, sr_out, &table, &phases);
   if (rc) return rc;
   if (sr_in == 2 * sr_out) {  // one table phase for every output: the symmetric-FIR decimator
     const int64_t ctas = (n_fix + kHalfOut - 1) / kHalfOut;
@@ -214,6 +342,15 @@ int mst_resample_f32(const float* d_in, int64_t n_in, int sr_in, int sr_out, flo
   }
   const int threads = 256;
   const int64_t blocks = (n_fix + threads - 1) / threads;
+  // MST_RS_NO_PHASES=1 (environment; tests and A/B runs): per-output table interpolation for every ratio
+  const char* no_phases = getenv("MST_RS_NO_PHASES");
+  if (phases->usable && !(no_phases && no_phases[0] == '1') && (double)n_fix * (double)phases->geom.p < 9.0e18) {
+    resample_phase_kernel<<<(unsigned)(blocks < 148 * 64 ? blocks : 148 * 64), threads, 0, s>>>(
+        d_in, n_in, d_out, n_out, n_fix, phases->d_w, phases->d_lims, phases->geom);
+    MST_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return MST_OK;
+  }
   resample_kernel<<<(unsigned)(blocks < 148 * 64 ? blocks : 148 * 64), threads, 0, s>>>(d_in, n_in, d_out, n_out, n_fix, table,
                                                                                  1.0 / ratio, scale, index_step);
   MST_CUDA_OK(cudaGetLastError());

@@ -416,6 +416,27 @@ def test_resample_kaiser_best(pkg, so, sn):
     assert_close(got, ref.astype(np.float64))
 
 
+@pytest.mark.parametrize("so,sn", [(48000, 44100), (22050, 44100), (44100, 16000), (8000, 22050), (44100, 48000), (44101, 44100)])
+def test_resample_phase_tables_match_per_output_interpolation(pkg, so, sn, monkeypatch):
+    """Rational ratios run resample_phase_kernel (tap weights precomputed per phase); MST_RS_NO_PHASES=1 forces the
+    per-output table interpolation.  Same taps, same float32 fma, same summation order: the two agree to rounding of the
+    phase position (1e-6), and both match the oracle; awkward lengths exercise the wing limits at both signal ends.
+    44101 -> 44100 has 44100 phases (> 2048): it always takes the per-output kernel."""
+    for n in (5, 130, 1000, 20011):
+        x = (clip(57, max(n, 1025), "noise")[:n] + 0.5).astype(np.float32)
+        monkeypatch.delenv("MST_RS_NO_PHASES", raising=False)
+        a = pkg.audio_io.resample(x, so, sn)
+        monkeypatch.setenv("MST_RS_NO_PHASES", "1")
+        b = pkg.audio_io.resample(x, so, sn)
+        monkeypatch.delenv("MST_RS_NO_PHASES", raising=False)
+        assert a.shape == b.shape == (int(np.ceil(n * sn / so)),)
+        scale = max(1.0, float(np.abs(b).max()))
+        assert np.abs(a - b).max() <= 2e-6 * scale, (n, np.abs(a - b).max())
+        if n <= 1000:
+            ref = oaudio.resample(x, so, sn)
+            assert np.abs(a - ref).max() <= 1e-5 * scale, (n, np.abs(a - ref).max())
+
+
 def test_resample_halving_edge_cases_and_mono_mix(pkg, gpu):
     """The decimate-by-2 FIR path (one table phase for every output) at awkward lengths, and librosa.to_mono."""
     for n in (2, 3, 100, 255, 1023, 4097):   # (n = 1 gives zero output samples: resampy itself raises there)
