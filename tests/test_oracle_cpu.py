@@ -410,3 +410,19 @@ def test_oracle_mel_filterbank_other_nfft(sr, n_fft, n_mels, built_libs):
     assert lib.mst_mel_filterbank_f32(sr, n_fft, n_mels, ctypes.c_double(0.0), ctypes.c_double(0.0),
                                       Wc.ctypes.data_as(ctypes.c_void_p)) == 0
     assert np.array_equal(Wc, W)
+
+
+def test_window_and_fft_size_validation():
+    """features._check_window: host-side argument checking shared by stft / melspectrogram / griffinlim (no GPU needed)."""
+    from ml_music_style_transfer_b200 import features as F
+    assert F._check_window("hann", None, 2048) == 2048 and F._check_window("hann", 1200, 2048) == 1200
+    for n_fft in (64, 512, 1024, 4096, 16384):
+        assert F._check_window("hann", None, n_fft) == n_fft
+    for n_fft in (1000, 32, 32768, 3000):
+        with pytest.raises(NotImplementedError):
+            F._check_window("hann", None, n_fft)
+    with pytest.raises(NotImplementedError):
+        F._check_window("hamming", None, 2048)
+    for wl in (0, 2049):
+        with pytest.raises(ValueError):
+            F._check_window("hann", wl, 2048)
