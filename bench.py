@@ -204,7 +204,8 @@ def run_ours(args):
     if not args.serial:
         from ml_music_style_transfer_b200.pipeline import DevicePipeline
         dpipe = DevicePipeline(n_clips, CLIP_LEN, notes_h, sr=SR, hop=HOP, n_mels=N_MELS, roll_fs=ROLL_FS, pitch_lo=PITCH_LO,
-                               n_keys=N_KEYS, gl_iters=GL_ITERS, n_chunks=args.step_chunks, device=device, plan=plan)
+                               n_keys=N_KEYS, gl_iters=GL_ITERS, n_chunks=args.step_chunks, n_streams=args.step_streams, device=device,
+                               plan=plan)
 
     def step():
         if dpipe is not None:
@@ -327,7 +328,7 @@ def run_ours(args):
         if not args.serial:
             sp = DevicePipeline(m, CLIP_LEN, tuple(a[:offs[m]] for a in notes_h[:4]) + (offs[:m + 1],), sr=SR, hop=HOP,
                                 n_mels=N_MELS, roll_fs=ROLL_FS, pitch_lo=PITCH_LO, n_keys=N_KEYS, gl_iters=GL_ITERS,
-                                n_chunks=max(1, args.step_chunks // world), device=device, plan=plan)
+                                n_chunks=max(1, args.step_chunks // world), n_streams=args.step_streams, device=device, plan=plan)
             step_s = lambda: sp.run(audio[:m * CLIP_LEN], S[:m * T_FRAMES * K])   # noqa: E731
         for _ in range(3):
             step_s()
@@ -693,7 +694,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--serial", action="store_true", help="time the three stages back to back on one stream instead of the "
                                                         "chunk-pipelined DevicePipeline schedule")
-    ap.add_argument("--step-chunks", type=int, default=32, help="chunks of the pipelined step (rotating over 4 streams)")
+    ap.add_argument("--step-chunks", type=int, default=32, help="chunks of the pipelined step (rotating over --step-streams streams)")
+    ap.add_argument("--step-streams", type=int, default=4, help="CUDA streams the chunks of the pipelined step rotate over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per GL-iteration launch (from profiles/)")
     args = ap.parse_args()
