@@ -116,6 +116,9 @@ int mst_mel_filterbank_f32(int sr, int n_fft, int n_mels, double fmin, double fm
 typedef struct mst_mel_plan mst_mel_plan_t;
 int mst_mel_plan_create(const float* h_weights, int n_mels, int n_bins, mst_mel_plan_t** out);
 void mst_mel_plan_destroy(mst_mel_plan_t* p);
+/* Workspace for the ring of split-precision power-spectrum rows between the STFT and the projection kernel: sized for
+ * THIS batch (at most 8 waves of 128-frame projection tiles, never more rows than the batch has frames); query it with the
+ * batch you are going to pass to mst_stft_mel_f32. */
 size_t mst_stft_mel_workspace_bytes(const mst_batch_t* batch, const mst_mel_plan_t* plan);
 int mst_stft_mel_f32(const float* d_audio, const mst_batch_t* batch, const mst_mel_plan_t* plan,
                      int apply_log1p, int layout, float* d_out, void* d_workspace, size_t workspace_bytes,

@@ -10,6 +10,7 @@
 // of the trimmed, reflect-padded signal; momentum update), one kernel per step, all state in the caller's workspace.
 #include <math.h>
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <vector>
 #include "mel_plan.cuh"
@@ -18,6 +19,7 @@
 namespace mst {
 
 constexpr int kGenThreads = 256;
+constexpr int kGenMaxSmem = 2 * (16384 / 2) * (int)sizeof(float2);  // two ping-pong buffers of the largest FFT (128 KB)
 
 struct GenGeom {
   int n_fft, M, logM, K, hop, pad_mode;  // M = n_fft / 2 (complex FFT length), K = M + 1 bins
@@ -244,8 +246,16 @@ static int launch_gen_stft(const float* d_audio, const mst_batch* b, int layout,
   int rc = gen_twiddles(g.n_fft, &tw);
   if (rc) return rc;
   const size_t smem = sizeof(float2) * 2 * (size_t)g.M;
-  if (smem > 48 * 1024)
-    MST_CUDA_OK(cudaFuncSetAttribute(gen_stft_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) {  // n_fft >= 8192: opt in once per device and instantiation (to the largest size served)
+    static std::atomic<bool> attr_set[64];
+    int dev = 0;
+    MST_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(MST_ERR_INVALID, "device index %d out of range", dev);
+    if (!attr_set[dev].load(std::memory_order_acquire)) {
+      MST_CUDA_OK(cudaFuncSetAttribute(gen_stft_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGenMaxSmem));
+      attr_set[dev].store(true, std::memory_order_release);
+    }
+  }
   const int64_t blocks = (int64_t)b->total_tiles * kWarpsPerCta;
   if (blocks > 0x7fffffff) return fail(MST_ERR_INVALID, "too many frames for one launch");
   gen_stft_kernel<MODE><<<(unsigned)blocks, kGenThreads, smem, s>>>(d_audio, b->d_clips, b->d_tile_clip, g, tw, b->d_window,
@@ -423,8 +433,15 @@ int generic_griffinlim(const float* d_S, int s_layout, int s_is_log1p_power, con
 
   const size_t smem = sizeof(float2) * 2 * (size_t)g.M;
   if (smem > 48 * 1024) {
-    MST_CUDA_OK(cudaFuncSetAttribute(gen_gl_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MST_CUDA_OK(cudaFuncSetAttribute(gen_gl_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static std::atomic<bool> attr_set[64];
+    int dev = 0;
+    MST_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(MST_ERR_INVALID, "device index %d out of range", dev);
+    if (!attr_set[dev].load(std::memory_order_acquire)) {
+      MST_CUDA_OK(cudaFuncSetAttribute(gen_gl_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGenMaxSmem));
+      MST_CUDA_OK(cudaFuncSetAttribute(gen_gl_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGenMaxSmem));
+      attr_set[dev].store(true, std::memory_order_release);
+    }
   }
   const int64_t blocks64 = (int64_t)b->total_tiles * kWarpsPerCta;
   if (blocks64 > 0x7fffffff) return fail(MST_ERR_INVALID, "too many frames for one launch");
