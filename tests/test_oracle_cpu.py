@@ -426,3 +426,33 @@ def test_window_and_fft_size_validation():
     for wl in (0, 2049):
         with pytest.raises(ValueError):
             F._check_window("hann", wl, 2048)
+
+
+@pytest.mark.parametrize("dtype,bits", [(np.int16, 16), (np.int32, 32), (np.uint8, 8), (np.float32, 32), (np.float64, 64)])
+@pytest.mark.parametrize("channels", [1, 2])
+def test_wav_decoders_match_scipy_wavfile(tmp_path, dtype, bits, channels):
+    """Independent pin of both RIFF decoders (oracle.audio.read_wav and the product's audio_io.read_wav): files written
+    by scipy.io.wavfile, samples compared with scipy's own read scaled the way soundfile/librosa.load scale them
+    (int16 / 2**15, int32 / 2**31, (uint8 - 128) / 128, floats as they are)."""
+    import scipy.io.wavfile as wavfile
+    from ml_music_style_transfer_b200 import audio_io
+    rng = np.random.default_rng(bits + channels)
+    n = 777
+    if np.issubdtype(dtype, np.floating):
+        data = (0.5 * rng.standard_normal((n, channels))).astype(dtype)
+        want = data.astype(np.float32)
+    else:
+        info = np.iinfo(dtype)
+        data = rng.integers(info.min, info.max, size=(n, channels), endpoint=True).astype(dtype)
+        if dtype == np.uint8:
+            want = (data.astype(np.float32) - 128.0) / 128.0
+        else:
+            want = (data.astype(np.float64) / float(2 ** (bits - 1))).astype(np.float32)
+    path = str(tmp_path / "s.wav")
+    wavfile.write(path, 48000, data if channels > 1 else data[:, 0])
+    sr_s, back_s = wavfile.read(path)
+    assert sr_s == 48000 and np.array_equal(back_s.reshape(n, channels), data)
+    for reader in (oaudio.read_wav, audio_io.read_wav):
+        x, sr = reader(path)
+        assert sr == 48000 and x.shape == (n, channels) and x.dtype == np.float32
+        assert np.array_equal(x, want), reader.__module__
