@@ -121,3 +121,53 @@ def test_bend_segments_host_logic():
     assert [(s[0], s[1], s[4], s[5]) for s in segs] == [(25, 50, 1, 1), (50, 60, 0, 1), (75, 90, -2, 0), (90, 100, 0, 0)]
     assert segs[0][2] == 0.0 and segs[1][2] == 0.5 and segs[2][2] == 0.0 and segs[3][2] == 100 * 2.0 / 8192.0
     assert all(s[3] == 1 - s[2] for s in segs)
+
+
+def test_reader_on_hand_assembled_file(tmp_path):
+    """A type-1 file assembled byte by byte from the SMF specification (not by the repo's writer): running status,
+    note-on with velocity 0 as note-off, a tempo change in track 0, program change, CC64, pitch bend, a sysex and an
+    unknown meta event in between, a two-byte variable-length delta.  480 ticks per quarter; 120 bpm until tick 960,
+    then 60 bpm: tick 480 = 0.5 s, 960 = 1.0 s, 1440 = 2.0 s, 1920 = 3.0 s."""
+    from ml_music_style_transfer_b200 import midi
+
+    def chunk(tag, body):
+        return tag + len(body).to_bytes(4, 'big') + body
+
+    track0 = (b'\x00\xFF\x03\x05tempo'                      # track name
+              b'\x00\xFF\x58\x04\x04\x02\x18\x08'           # time signature (ignored)
+              b'\x87\x40\xFF\x51\x03\x0F\x42\x40'           # delta 960 (0x87 0x40): tempo 1 000 000 us/quarter = 60 bpm
+              b'\x00\xFF\x2F\x00')
+    track1 = (b'\x00\xC0\x05'                               # program 5 on channel 0
+              b'\x00\xF0\x03\x7E\x7F\xF7'                   # sysex, 3 data bytes
+              b'\x00\x90\x3C\x64'                           # tick 0: note-on 60 vel 100
+              b'\x00\x40\x50'                               # running status: note-on 64 vel 80
+              b'\x83\x60\x3C\x00'                           # delta 480 (0x83 0x60): running status note-on 60 vel 0 = note-off at 0.5 s
+              b'\x00\xB0\x40\x7F'                           # CC64 = 127 at tick 480
+              b'\x83\x60\x80\x40\x00'                       # tick 960: note-off 64 -> 1.0 s
+              b'\x00\xFF\x7F\x02\x00\x01'                   # sequencer-specific meta (unknown to the reader)
+              b'\x83\x60\xE0\x00\x50'                       # tick 1440 = 2.0 s: pitch bend 0x50 << 7 = 10240 -> +2048
+              b'\x00\x90\x43\x7F'                           # note-on 67 vel 127 at 2.0 s
+              b'\x83\x60\x80\x43\x40'                       # tick 1920 = 3.0 s: note-off 67
+              b'\x00\xB0\x40\x00'                           # CC64 = 0 at 3.0 s
+              b'\x00\xFF\x2F\x00')
+    data = chunk(b'MThd', (1).to_bytes(2, 'big') + (2).to_bytes(2, 'big') + (480).to_bytes(2, 'big')) + \
+        chunk(b'MTrk', track0) + chunk(b'MTrk', track1)
+    path = str(tmp_path / "hand.mid")
+    with open(path, 'wb') as f:
+        f.write(data)
+    mf = midi.read_midi_file(path)
+    assert mf.resolution == 480 and len(mf.instruments) == 1
+    ins = mf.instruments[0]
+    assert ins.program == 5 and not ins.is_drum
+    notes = sorted(zip(ins.pitch, ins.velocity, ins.start, ins.end))
+    assert notes == [(60, 100, 0.0, 0.5), (64, 80, 0.0, 1.0), (67, 127, 2.0, 3.0)]
+    assert ins.control_changes == [(64, 127, 0.5), (64, 0, 3.0)]
+    assert ins.pitch_bends == [(2048, 2.0)]
+    assert mf.get_end_time() == 3.0
+    # the oracle's roll of that instrument: the pedal goes down at 0.5 s, exactly when 60 ends (not sustained: the
+    # running maximum starts inside the span), while 64 is sounding and is held; the bend only acts from 2.0 s on
+    from oracle import pianoroll as opr
+    roll = opr.instrument_piano_roll(ins, 100)
+    assert roll.shape == (128, 300)
+    assert (roll[60, 0:50] == 100).all() and (roll[60, 50:200] == 0).all() and (roll[64, 0:200] == 80).all()
+    assert roll[67, 200:].sum() > 0 and roll[68, 200:].sum() > 0   # +0.5 semitone: 67 is split between rows 67 and 68
